@@ -1,0 +1,855 @@
+// fv3atm_b200: context, host-side orchestration and the C-ABI (include/fv3tracer.h) of libfv3tracer.so.
+//
+// Host logic restated from the reference's tracer_2d driver (atmos_cubed_sphere/model/fv_tracer2d.F90:
+// 432-457 nsplt/ksplt, :496-566 sub-step loop) and from the j-loop dispatch of Lagrangian_to_Eulerian
+// (model/fv_mapz.F90:407-426).  The cubed-sphere mosaic is the 12-contact table of tools/fv_mp_mod.F90:581-629.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fv3tracer.h"
+#include "fv3t_advect.cuh"
+#include "fv3t_remap.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- mosaic topology ------------------------------------------------------------------------------
+enum { EW = 0, EE = 1, ES = 2, EN = 3 };
+struct EdgeMap {
+  int nbr_tile, nbr_edge;  // 0-based tile
+  int A[2][2], b[2];       // halo cell (i,j) of this tile -> cell (A(i,j)+b) of nbr_tile, 1-based cells
+};
+
+struct Line4 {
+  int is, ie, js, je;
+};
+
+void edge_of(const Line4& l, int n, int& edge, int p0[2], int d[2], int out[2]) {
+  p0[0] = l.is;
+  p0[1] = l.js;
+  d[0] = (l.ie > l.is) - (l.ie < l.is);
+  d[1] = (l.je > l.js) - (l.je < l.js);
+  if (l.is == l.ie) {
+    edge = (l.is == n) ? EE : EW;
+    out[0] = (edge == EE) ? 1 : -1;
+    out[1] = 0;
+  } else {
+    edge = (l.js == n) ? EN : ES;
+    out[0] = 0;
+    out[1] = (edge == EN) ? 1 : -1;
+  }
+}
+
+// maps[tile][edge] for the six-tile cubed sphere
+void build_edge_maps(int n, EdgeMap maps[6][4]) {
+  const int nx = n, ny = n;
+  struct C {
+    int t1, t2;
+    Line4 l1, l2;
+  };
+  const C contacts[12] = {
+      {1, 2, {nx, nx, 1, ny}, {1, 1, 1, ny}},   {1, 3, {1, nx, ny, ny}, {1, 1, ny, 1}},   {1, 5, {1, 1, 1, ny}, {nx, 1, ny, ny}},
+      {1, 6, {1, nx, 1, 1}, {1, nx, ny, ny}},   {2, 3, {1, nx, ny, ny}, {1, nx, 1, 1}},   {2, 4, {nx, nx, 1, ny}, {nx, 1, 1, 1}},
+      {2, 6, {1, nx, 1, 1}, {nx, nx, ny, 1}},   {3, 4, {nx, nx, 1, ny}, {1, 1, 1, ny}},   {3, 5, {1, nx, ny, ny}, {1, 1, ny, 1}},
+      {4, 5, {1, nx, ny, ny}, {1, nx, 1, 1}},   {4, 6, {nx, nx, 1, ny}, {nx, 1, 1, 1}},   {5, 6, {nx, nx, 1, ny}, {1, 1, 1, ny}},
+  };
+  for (const C& c : contacts) {
+    int e1, e2, p1[2], p2[2], d1[2], d2[2], o1[2], o2[2];
+    edge_of(c.l1, n, e1, p1, d1, o1);
+    edge_of(c.l2, n, e2, p2, d2, o2);
+    for (int side = 0; side < 2; ++side) {
+      const int ta = side ? c.t2 : c.t1, tb = side ? c.t1 : c.t2;
+      const int ea = side ? e2 : e1, eb = side ? e1 : e2;
+      const int* pa = side ? p2 : p1;
+      const int* pb = side ? p1 : p2;
+      const int* da = side ? d2 : d1;
+      const int* db = side ? d1 : d2;
+      const int* oa = side ? o2 : o1;
+      const int* ob = side ? o1 : o2;
+      EdgeMap& m = maps[ta - 1][ea];
+      m.nbr_tile = tb - 1;
+      m.nbr_edge = eb;
+      const int inb[2] = {-ob[0], -ob[1]};
+      for (int r = 0; r < 2; ++r)
+        for (int cc = 0; cc < 2; ++cc) m.A[r][cc] = db[r] * da[cc] + inb[r] * oa[cc];
+      for (int r = 0; r < 2; ++r) m.b[r] = pb[r] - inb[r] - (m.A[r][0] * pa[0] + m.A[r][1] * pa[1]);
+    }
+  }
+}
+
+// canonical order of the halo strip beyond `edge`: depth m = 1..3 outer, position s = 1..n inner
+inline void halo_cell(int edge, int n, int m, int s, int& i, int& j) {
+  switch (edge) {
+    case EW: i = 1 - m; j = s; break;
+    case EE: i = n + m; j = s; break;
+    case ES: i = s; j = 1 - m; break;
+    default: i = s; j = n + m; break;
+  }
+}
+
+enum KClass { KC_ADVECT = 0, KC_REMAP = 1, KC_HALO = 2, KC_CMAX = 3, KC_SCALE = 4, KC_N = 5 };
+
+template <class T> struct Impl {
+  fv3t_dims d{};
+  int n = 0, npz = 0, nqmax = 0, nt = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // device state
+  T *q[2] = {nullptr, nullptr}, *dp1 = nullptr, *mfx = nullptr, *mfy = nullptr, *cx = nullptr, *cy = nullptr, *pe = nullptr,
+    *delp = nullptr;
+  T *area = nullptr, *rarea = nullptr, *dx = nullptr, *dy = nullptr, *dxa = nullptr, *dya = nullptr, *sin_sg = nullptr;
+  T *ak = nullptr, *bk = nullptr, *cmax_t = nullptr;
+  T ptop = T(0);
+  int *ksplt_d = nullptr, *par_d = nullptr, *kord_d = nullptr, *halo_dst = nullptr, *halo_src = nullptr;
+  int halo_len = 0;
+  int* strip_idx[6][4] = {};  // per local tile / edge: device index lists (3n) for pack (src cells) and unpack (halo cells)
+  int* strip_halo[6][4] = {};
+  EdgeMap maps[6][4];
+  int local_of[6];  // global tile (0-based) -> local slot or -1
+  // host state
+  std::vector<int> ksplt, par;
+  std::vector<T> cmax_h;
+  int nsplt = 1, nq_cur = 0;
+  bool have_vertical = false;
+  uint64_t launches = 0;
+  std::mutex row_mutex;
+  T* row_buf = nullptr;  // staging for the row-granular mapn_tracer entry
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool prof = false;
+  float prof_ms[KC_N] = {};
+  int prof_n[KC_N] = {};
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+
+  size_t plane() const { return (size_t)(n + 6) * (n + 6); }
+  size_t sz_q(int nq) const { return plane() * npz * nq; }
+  size_t sz_c() const { return plane() * npz; }
+  size_t sz_cx() const { return (size_t)(n + 1) * (n + 6) * npz; }
+  size_t sz_mf() const { return (size_t)(n + 1) * n * npz; }
+  size_t sz_pe() const { return (size_t)(n + 2) * (npz + 1) * (n + 2); }
+  size_t field_elems(int f, int nq) const {
+    switch (f) {
+      case FV3T_Q: return sz_q(nq) * nt;
+      case FV3T_DP1:
+      case FV3T_DELP: return sz_c() * nt;
+      case FV3T_MFX:
+      case FV3T_MFY: return sz_mf() * nt;
+      case FV3T_CX:
+      case FV3T_CY: return sz_cx() * nt;
+      case FV3T_PE: return sz_pe() * nt;
+    }
+    return 0;
+  }
+  T* field_ptr(int f) {
+    switch (f) {
+      case FV3T_Q: return q[0];
+      case FV3T_DP1: return dp1;
+      case FV3T_MFX: return mfx;
+      case FV3T_MFY: return mfy;
+      case FV3T_CX: return cx;
+      case FV3T_CY: return cy;
+      case FV3T_PE: return pe;
+      case FV3T_DELP: return delp;
+    }
+    return nullptr;
+  }
+
+  void kbegin() {
+    if (prof) cudaEventRecord(pe0, stream);
+  }
+  void kend(int kc) {
+    ++launches;
+    if (prof) {
+      cudaEventRecord(pe1, stream);
+      cudaEventSynchronize(pe1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, pe0, pe1);
+      prof_ms[kc] += ms;
+      prof_n[kc] += 1;
+    }
+  }
+
+  int create(const fv3t_dims* dims, const T* const* g /*7 ptrs*/, int dev, void* strm);
+  int destroy();
+  int upload(int f, const T* h, int nq);
+  int download(int f, T* h, int nq);
+  int begin(int nq, int q_split, T* cmax_local);
+  int set_cmax(const T* cmax_global, int q_split, int* nsplt_out);
+  int halo_local(int it);
+  int halo_pack(int it, int lt, int edge, T* buf, bool unpack);
+  int substep(int it, int hord, T lim_fac);
+  int finish();
+  int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
+  int remap_resident(int nq, const int* kord, int fill, int j_first, int j_count);
+};
+
+template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g, int dev, void* strm) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("fv3tracer: no CUDA device available (there is no CPU fallback)");
+  if (dev < 0 || dev >= ndev) return fail("fv3tracer: device %d out of range (%d devices)", dev, ndev);
+  d = *dims;
+  n = dims->npx - 1;
+  npz = dims->npz;
+  nqmax = dims->nq_max;
+  nt = dims->ntiles;
+  device = dev;
+  if (n < 8) return fail("fv3tracer: npx-1 = %d too small (need >= 8 cells per tile edge)", n);
+  if (npz < 6 || npz > 128) return fail("fv3tracer: npz = %d outside the supported range 6..128", npz);
+  if (nt < 1 || nt > 6) return fail("fv3tracer: ntiles = %d outside 1..6", nt);
+  if (nqmax < 1) return fail("fv3tracer: nq_max must be >= 1");
+  for (int t = 0; t < 6; ++t) local_of[t] = -1;
+  for (int s = 0; s < nt; ++s) {
+    const int gt = dims->tile_id[s] - 1;
+    if (gt < 0 || gt > 5 || local_of[gt] >= 0) return fail("fv3tracer: bad tile_id[%d] = %d", s, dims->tile_id[s]);
+    local_of[gt] = s;
+  }
+  CK(cudaSetDevice(dev));
+  if (strm) {
+    stream = (cudaStream_t)strm;
+  } else {
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+  }
+  build_edge_maps(n, maps);
+  auto dalloc = [&](T** p, size_t elems) -> cudaError_t { return cudaMalloc((void**)p, elems * sizeof(T)); };
+  CK(dalloc(&q[0], sz_q(nqmax) * nt));
+  CK(dalloc(&q[1], sz_q(nqmax) * nt));
+  CK(dalloc(&dp1, sz_c() * nt));
+  CK(dalloc(&delp, sz_c() * nt));
+  CK(dalloc(&mfx, sz_mf() * nt));
+  CK(dalloc(&mfy, sz_mf() * nt));
+  CK(dalloc(&cx, sz_cx() * nt));
+  CK(dalloc(&cy, sz_cx() * nt));
+  CK(dalloc(&pe, sz_pe() * nt));
+  CK(cudaMemsetAsync(q[0], 0, sz_q(nqmax) * nt * sizeof(T), stream));
+  CK(cudaMemsetAsync(q[1], 0, sz_q(nqmax) * nt * sizeof(T), stream));
+  CK(cudaMemsetAsync(delp, 0, sz_c() * nt * sizeof(T), stream));
+  const size_t pl = plane();
+  const size_t gsz[7] = {pl, pl, (size_t)(n + 6) * (n + 7), (size_t)(n + 7) * (n + 6), pl, pl, pl * 5};
+  T** gp[7] = {&area, &rarea, &dx, &dy, &dxa, &dya, &sin_sg};
+  for (int a = 0; a < 7; ++a) {
+    CK(dalloc(gp[a], gsz[a] * nt));
+    CK(cudaMemcpyAsync(*gp[a], g[a], gsz[a] * nt * sizeof(T), cudaMemcpyHostToDevice, stream));
+  }
+  CK(dalloc(&ak, npz + 1));
+  CK(dalloc(&bk, npz + 1));
+  CK(dalloc(&cmax_t, (size_t)nt * npz));
+  CK(cudaMalloc((void**)&ksplt_d, npz * sizeof(int)));
+  CK(cudaMalloc((void**)&par_d, npz * sizeof(int)));
+  CK(cudaMalloc((void**)&kord_d, nqmax * sizeof(int)));
+  CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
+  ksplt.assign(npz, 1);
+  par.assign(npz, 0);
+  cmax_h.assign((size_t)nt * npz, T(0));
+
+  // halo tables: local gathers (both tiles resident) + per-edge strips for remote exchange
+  std::vector<int> hd, hs;
+  const int nd = n + 6;
+  for (int s = 0; s < nt; ++s) {
+    const int gt = dims->tile_id[s] - 1;
+    for (int e = 0; e < 4; ++e) {
+      const EdgeMap& m = maps[gt][e];
+      std::vector<int> my_halo(3 * n), my_src(3 * n);
+      // cells of THIS tile that the neighbour across edge e needs, in the neighbour's canonical halo order
+      const EdgeMap& back = maps[m.nbr_tile][m.nbr_edge];
+      for (int mm = 1; mm <= 3; ++mm)
+        for (int ss = 1; ss <= n; ++ss) {
+          int i, j;
+          halo_cell(e, n, mm, ss, i, j);
+          my_halo[(mm - 1) * n + (ss - 1)] = (j + 2) * nd + (i + 2);
+          const int ip = m.A[0][0] * i + m.A[0][1] * j + m.b[0];
+          const int jp = m.A[1][0] * i + m.A[1][1] * j + m.b[1];
+          if (local_of[m.nbr_tile] >= 0) {
+            hd.push_back((s * nd + (j + 2)) * nd + (i + 2));
+            hs.push_back((local_of[m.nbr_tile] * nd + (jp + 2)) * nd + (ip + 2));
+          }
+          int bi, bj;
+          halo_cell(m.nbr_edge, n, mm, ss, bi, bj);
+          const int si = back.A[0][0] * bi + back.A[0][1] * bj + back.b[0];
+          const int sj = back.A[1][0] * bi + back.A[1][1] * bj + back.b[1];
+          my_src[(mm - 1) * n + (ss - 1)] = (sj + 2) * nd + (si + 2);
+        }
+      CK(cudaMalloc((void**)&strip_halo[s][e], 3 * n * sizeof(int)));
+      CK(cudaMalloc((void**)&strip_idx[s][e], 3 * n * sizeof(int)));
+      CK(cudaMemcpyAsync(strip_halo[s][e], my_halo.data(), 3 * n * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(strip_idx[s][e], my_src.data(), 3 * n * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));  // vectors go out of scope
+    }
+  }
+  halo_len = (int)hd.size();
+  if (halo_len) {
+    CK(cudaMalloc((void**)&halo_dst, halo_len * sizeof(int)));
+    CK(cudaMalloc((void**)&halo_src, halo_len * sizeof(int)));
+    CK(cudaMemcpyAsync(halo_dst, hd.data(), halo_len * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(halo_src, hs.data(), halo_len * sizeof(int), cudaMemcpyHostToDevice, stream));
+  }
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaEventCreate(&pe0));
+  CK(cudaEventCreate(&pe1));
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+template <class T> int Impl<T>::destroy() {
+  cudaSetDevice(device);
+  cudaStreamSynchronize(stream);
+  void* ptrs[] = {q[0], q[1], dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+                  ksplt_d, par_d, kord_d, halo_dst, halo_src, row_buf};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (int s = 0; s < 6; ++s)
+    for (int e = 0; e < 4; ++e) {
+      if (strip_idx[s][e]) cudaFree(strip_idx[s][e]);
+      if (strip_halo[s][e]) cudaFree(strip_halo[s][e]);
+    }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (pe0) cudaEventDestroy(pe0);
+  if (pe1) cudaEventDestroy(pe1);
+  if (own_stream) cudaStreamDestroy(stream);
+  return 0;
+}
+
+template <class T> int Impl<T>::upload(int f, const T* h, int nq) {
+  T* dptr = field_ptr(f);
+  if (!dptr) return fail("fv3tracer: unknown field %d", f);
+  if (f == FV3T_Q && (nq < 1 || nq > nqmax)) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpyAsync(dptr, h, field_elems(f, nq) * sizeof(T), cudaMemcpyHostToDevice, stream));
+  if (f == FV3T_Q) {
+    nq_cur = nq;
+    std::fill(par.begin(), par.end(), 0);
+    CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
+  }
+  return 0;
+}
+
+template <class T> int Impl<T>::download(int f, T* h, int nq) {
+  T* dptr = field_ptr(f);
+  if (!dptr) return fail("fv3tracer: unknown field %d", f);
+  CK(cudaSetDevice(device));
+  if (f != FV3T_Q) {
+    CK(cudaMemcpyAsync(h, dptr, field_elems(f, nq) * sizeof(T), cudaMemcpyDeviceToHost, stream));
+  } else {
+    if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+    // gather every level from the ping-pong buffer it currently lives in
+    const size_t pl = plane();
+    bool any = false;
+    for (int k = 0; k < npz; ++k) any |= par[k] != 0;
+    if (!any) {
+      CK(cudaMemcpyAsync(h, q[0], sz_q(nq) * nt * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    } else {
+      for (int t = 0; t < nt; ++t)
+        for (int iq = 0; iq < nq; ++iq)
+          for (int k = 0; k < npz; ++k) {
+            const size_t off = (((size_t)t * nq + iq) * npz + k) * pl;
+            CK(cudaMemcpyAsync(h + off, q[par[k]] + off, pl * sizeof(T), cudaMemcpyDeviceToHost, stream));
+          }
+    }
+  }
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// steps A-B up to the local cmax (fv_tracer2d.F90:387-427); xfx/yfx are not materialised (see fv3t_advect.cuh)
+template <class T> int Impl<T>::begin(int nq, int q_split, T* cmax_local) {
+  if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  CK(cudaSetDevice(device));
+  nq_cur = nq;
+  // a previous tracer_2d without a remap may have left levels in buffer 1
+  bool any = false;
+  for (int k = 0; k < npz; ++k) any |= par[k] != 0;
+  if (any) {
+    for (int t = 0; t < nt; ++t) {
+      const long total = (long)sz_q(nq);
+      kbegin();
+      fv3t::k_copy_levels<T><<<1184, 256, 0, stream>>>(q[0] + (size_t)t * total, q[1] + (size_t)t * total, par_d, (long)plane(), npz,
+                                                       total);
+      kend(KC_SCALE);
+    }
+    std::fill(par.begin(), par.end(), 0);
+    CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
+  }
+  if (q_split == 0) {
+    kbegin();
+    fv3t::k_cmax<T><<<nt * npz, 512, 0, stream>>>(cx, cy, sin_sg, cmax_t, n, npz);
+    kend(KC_CMAX);
+    CK(cudaMemcpyAsync(cmax_h.data(), cmax_t, sizeof(T) * nt * npz, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (cmax_local) {
+      for (int k = 0; k < npz; ++k) {
+        T c = cmax_h[k];
+        for (int t = 1; t < nt; ++t) c = std::max(c, cmax_h[(size_t)t * npz + k]);
+        cmax_local[k] = c;
+      }
+    }
+  } else if (cmax_local) {
+    for (int k = 0; k < npz; ++k) cmax_local[k] = T(0);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// mp_reduce_max result -> nsplt, ksplt (fv_tracer2d.F90:432-457).  q_split /= 0: the reference reads an
+// unset cmax for ksplt; defined here as ksplt(k) = nsplt.
+template <class T> int Impl<T>::set_cmax(const T* cmax_global, int q_split, int* nsplt_out) {
+  CK(cudaSetDevice(device));
+  if (q_split == 0) {
+    T c_global = cmax_global[0];
+    if (npz != 1)
+      for (int k = 1; k < npz; ++k) c_global = std::max(cmax_global[k], c_global);
+    nsplt = (int)(T(1) + c_global);
+  } else {
+    nsplt = q_split;
+  }
+  for (int k = 0; k < npz; ++k) ksplt[k] = 1;
+  if (nsplt != 1)
+    for (int k = 0; k < npz; ++k) ksplt[k] = (q_split == 0) ? (int)(T(1) + cmax_global[k]) : nsplt;
+  CK(cudaMemcpyAsync(ksplt_d, ksplt.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+  if (nsplt_out) *nsplt_out = nsplt;
+  return 0;
+}
+
+template <class T> int Impl<T>::halo_local(int it) {
+  if (!halo_len) return 0;
+  CK(cudaSetDevice(device));
+  dim3 grid((halo_len + 255) / 256, nq_cur * npz);
+  kbegin();
+  fv3t::k_halo_fill<T><<<grid, 256, 0, stream>>>(q[(it - 1) & 1], halo_dst, halo_src, halo_len, n, npz, nq_cur, ksplt_d, it);
+  kend(KC_HALO);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class T>
+__global__ void k_strip(T* __restrict__ q, T* __restrict__ buf, const int* __restrict__ idx, int n, int npz, int nq,
+                        const int* __restrict__ ksplt, int it, int unpack) {
+  const long plane = (long)(n + 6) * (n + 6);
+  const int pl = blockIdx.y;  // iq*npz + kz
+  if (it > ksplt[pl % npz]) return;
+  const int len = 3 * n;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < len; e += gridDim.x * blockDim.x) {
+    if (unpack)
+      q[(long)pl * plane + idx[e]] = buf[(long)pl * len + e];
+    else
+      buf[(long)pl * len + e] = q[(long)pl * plane + idx[e]];
+  }
+}
+
+template <class T> int Impl<T>::halo_pack(int it, int lt, int edge, T* buf, bool unpack) {
+  if (lt < 0 || lt >= nt || edge < 0 || edge > 3) return fail("fv3tracer: bad tile/edge %d/%d", lt, edge);
+  CK(cudaSetDevice(device));
+  dim3 grid((3 * n + 255) / 256, nq_cur * npz);
+  T* qt = q[(it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
+  kbegin();
+  k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, unpack ? strip_halo[lt][edge] : strip_idx[lt][edge], n, npz, nq_cur, ksplt_d, it,
+                                       unpack ? 1 : 0);
+  kend(KC_HALO);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class T, int OI, int OO> int launch_advect(Impl<T>& c, const fv3t::AdvParams<T>& p) {
+  constexpr int TX = 32, TY = 16;
+  using TL = fv3t::AdvTile<TX, TY>;
+  auto kern = fv3t::k_advect<T, OI, OO, TX, TY>;
+  const size_t smem = TL::template smem_bytes<T>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((c.n + TX - 1) / TX, (c.n + TY - 1) / TY, c.nt * c.npz);
+  c.kbegin();
+  kern<<<grid, TL::NTHREADS, smem, c.stream>>>(p);
+  c.kend(KC_ADVECT);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// one pass of the `it` loop body (fv_tracer2d.F90:503-556) for the resident tiles
+template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
+  CK(cudaSetDevice(device));
+  fv3t::AdvParams<T> p;
+  p.qin = q[(it - 1) & 1];
+  p.qout = q[it & 1];
+  p.dp1 = dp1;
+  p.mfx = mfx;
+  p.mfy = mfy;
+  p.cx = cx;
+  p.cy = cy;
+  p.g = fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg};
+  p.ksplt = ksplt_d;
+  p.n = n;
+  p.npz = npz;
+  p.nq = nq_cur;
+  p.ntiles = nt;
+  p.it = it;
+  p.nsplt = nsplt;
+  p.lim_fac = lim_fac;
+  int rc;
+  switch (hord) {
+    case 8: rc = launch_advect<T, 8, 8>(*this, p); break;
+    case 10: rc = launch_advect<T, 8, 10>(*this, p); break;  // ord_in = 8 when hord == 10 (tp_core.F90:157-161)
+    case 9: rc = launch_advect<T, 9, 9>(*this, p); break;
+    case 7: rc = launch_advect<T, 7, 7>(*this, p); break;
+    case 11: rc = launch_advect<T, 11, 11>(*this, p); break;
+    case 12: rc = launch_advect<T, 12, 12>(*this, p); break;
+    case 13: rc = launch_advect<T, 13, 13>(*this, p); break;
+    case 5: rc = launch_advect<T, 5, 5>(*this, p); break;
+    case -5: rc = launch_advect<T, -5, -5>(*this, p); break;
+    case 6: rc = launch_advect<T, 6, 6>(*this, p); break;
+    case 1: rc = launch_advect<T, 1, 1>(*this, p); break;
+    case 2: rc = launch_advect<T, 2, 2>(*this, p); break;
+    case 3: rc = launch_advect<T, 3, 3>(*this, p); break;
+    case 4: rc = launch_advect<T, 4, 4>(*this, p); break;
+    default: return fail("fv3tracer: hord_tr = %d is not a scheme of xppm/yppm", hord);
+  }
+  if (rc) return rc;
+  for (int k = 0; k < npz; ++k)
+    if (it <= ksplt[k]) par[k] = it & 1;
+  return 0;
+}
+
+template <class T> int Impl<T>::finish() {
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpyAsync(par_d, par.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
+  if (nsplt != 1) {
+    struct A {
+      T* p;
+      long plane;
+      size_t total;
+    } arr[4] = {{cx, (long)(n + 1) * (n + 6), sz_cx() * nt},
+                {cy, (long)(n + 1) * (n + 6), sz_cx() * nt},
+                {mfx, (long)(n + 1) * n, sz_mf() * nt},
+                {mfy, (long)(n + 1) * n, sz_mf() * nt}};
+    for (auto& a : arr) {
+      kbegin();
+      fv3t::k_scale_frac<T><<<1184, 256, 0, stream>>>(a.p, ksplt_d, a.plane, npz, (long)a.total);
+      kend(KC_SCALE);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class T> int Impl<T>::tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out) {
+  if (nt != 6) return fail("fv3tracer: tracer_2d needs all six tiles resident (ntiles = %d); use the *_begin/halo/substep calls", nt);
+  std::vector<T> cm(npz);
+  int rc = begin(nq, q_split, cm.data());
+  if (rc) return rc;
+  rc = set_cmax(cm.data(), q_split, nsplt_out);
+  if (rc) return rc;
+  for (int it = 1; it <= nsplt; ++it) {
+    rc = halo_local(it);
+    if (rc) return rc;
+    rc = substep(it, hord, lim_fac);
+    if (rc) return rc;
+  }
+  return finish();
+}
+
+template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill, int j_first, int j_count) {
+  if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  if (!have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpyAsync(kord_d, kord, nq * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(par_d, par.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
+  fv3t::RemapParams<T> p;
+  p.q0 = q[0];
+  p.q1 = q[1];
+  p.qout = q[0];
+  p.par = par_d;
+  p.pe = pe;
+  p.ak = ak;
+  p.bk = bk;
+  p.delp = delp;
+  p.kord = kord_d;
+  p.ptop = ptop;
+  p.n = n;
+  p.km = npz;
+  p.nq = nq;
+  p.ntiles = nt;
+  p.fill = fill;
+  p.j_first = j_first;
+  p.j_count = j_count;
+  const int cols = n * j_count;
+  dim3 grid((cols + 63) / 64, nt);
+  kbegin();
+  if (npz <= 64)
+    fv3t::k_remap<T, 64><<<grid, 64, 0, stream>>>(p);
+  else
+    fv3t::k_remap<T, 128><<<grid, 64, 0, stream>>>(p);
+  kend(KC_REMAP);
+  CK(cudaGetLastError());
+  if (j_count == n) {
+    std::fill(par.begin(), par.end(), 0);
+    CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
+  }
+  nq_cur = nq;
+  return 0;
+}
+
+}  // namespace
+
+// ---- the opaque handle ------------------------------------------------------------------------------
+struct fv3t_ctx {
+  int prec;  // 4 or 8
+  Impl<float>* f32;
+  Impl<double>* f64;
+};
+
+extern "C" const char* fv3t_last_error(void) { return g_err.c_str(); }
+extern "C" int fv3t_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+#define IMPL(ctx, P) ((ctx) && (ctx)->P ? (ctx)->P : nullptr)
+#define NEED(ctx, P)                                                                                   \
+  auto* I = IMPL(ctx, P);                                                                              \
+  if (!I) return fail("fv3tracer: null context or precision mismatch (context is %s)", (ctx) ? ((ctx)->prec == 8 ? "f64" : "f32") : "null")
+
+#define FV3T_DEFINE(P, REAL)                                                                                                   \
+  extern "C" int fv3t_##P##_create(fv3t_ctx** ctx, const fv3t_dims* dims, const fv3t_##P##_grid* grid, int device,             \
+                                   void* stream) {                                                                             \
+    if (!ctx || !dims || !grid) return fail("fv3tracer: null argument");                                                       \
+    auto* I = new Impl<REAL>();                                                                                                \
+    const REAL* g[7] = {grid->area, grid->rarea, grid->dx, grid->dy, grid->dxa, grid->dya, grid->sin_sg};                      \
+    const int rc = I->create(dims, g, device, stream);                                                                         \
+    if (rc) {                                                                                                                  \
+      I->destroy();                                                                                                            \
+      delete I;                                                                                                                \
+      return rc;                                                                                                               \
+    }                                                                                                                          \
+    auto* c = new fv3t_ctx{(int)sizeof(REAL), nullptr, nullptr};                                                               \
+    c->P = I;                                                                                                                  \
+    *ctx = c;                                                                                                                  \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_upload(fv3t_ctx* ctx, int field, const REAL* host, int nq) {                                       \
+    NEED(ctx, P);                                                                                                              \
+    return I->upload(field, host, nq);                                                                                         \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_download(fv3t_ctx* ctx, int field, REAL* host, int nq) {                                           \
+    NEED(ctx, P);                                                                                                              \
+    return I->download(field, host, nq);                                                                                       \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_set_vertical(fv3t_ctx* ctx, const REAL* ak, const REAL* bk, REAL ptop) {                           \
+    NEED(ctx, P);                                                                                                              \
+    CK(cudaSetDevice(I->device));                                                                                              \
+    CK(cudaMemcpyAsync(I->ak, ak, (I->npz + 1) * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                            \
+    CK(cudaMemcpyAsync(I->bk, bk, (I->npz + 1) * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                            \
+    CK(cudaStreamSynchronize(I->stream));                                                                                      \
+    I->ptop = ptop;                                                                                                            \
+    I->have_vertical = true;                                                                                                   \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d_resident(fv3t_ctx* ctx, int nq, int hord, int q_split, REAL lim_fac, int* nsplt_out) {   \
+    NEED(ctx, P);                                                                                                              \
+    return I->tracer_2d_resident(nq, hord, q_split, lim_fac, nsplt_out);                                                       \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_remap_tracers_resident(fv3t_ctx* ctx, int nq, const int* kord_tr, int fill) {                      \
+    NEED(ctx, P);                                                                                                              \
+    return I->remap_resident(nq, kord_tr, fill, 0, I->n);                                                                      \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,     \
+                                      int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out,            \
+                                      int* ksplt_out) {                                                                        \
+    NEED(ctx, P);                                                                                                              \
+    (void)nord_tr;                                                                                                             \
+    if (trdm > REAL(1.e-4)) return fail("fv3tracer: tracer del-2 damping (trdm2 > 1e-4, deln_flux) is not supported");        \
+    int rc;                                                                                                                    \
+    if ((rc = I->upload(FV3T_Q, q, nq))) return rc;                                                                            \
+    if ((rc = I->upload(FV3T_DP1, dp1, nq))) return rc;                                                                        \
+    if ((rc = I->upload(FV3T_MFX, mfx, nq))) return rc;                                                                        \
+    if ((rc = I->upload(FV3T_MFY, mfy, nq))) return rc;                                                                        \
+    if ((rc = I->upload(FV3T_CX, cx, nq))) return rc;                                                                          \
+    if ((rc = I->upload(FV3T_CY, cy, nq))) return rc;                                                                          \
+    if ((rc = I->tracer_2d_resident(nq, hord, q_split, lim_fac, nsplt_out))) return rc;                                        \
+    if (ksplt_out) std::memcpy(ksplt_out, I->ksplt.data(), sizeof(int) * I->npz);                                              \
+    if ((rc = I->download(FV3T_Q, q, nq))) return rc;                                                                          \
+    if ((rc = I->download(FV3T_DP1, dp1, nq))) return rc;                                                                      \
+    if (I->nsplt != 1) {                                                                                                       \
+      if ((rc = I->download(FV3T_MFX, mfx, nq))) return rc;                                                                    \
+      if ((rc = I->download(FV3T_MFY, mfy, nq))) return rc;                                                                    \
+      if ((rc = I->download(FV3T_CX, cx, nq))) return rc;                                                                      \
+      if ((rc = I->download(FV3T_CY, cy, nq))) return rc;                                                                      \
+    }                                                                                                                          \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_remap_tracers(fv3t_ctx* ctx, const REAL* pe, const REAL* ak, const REAL* bk, REAL ptop, REAL* q,   \
+                                          REAL* delp, int nq, const int* kord_tr, int fill) {                                  \
+    NEED(ctx, P);                                                                                                              \
+    int rc;                                                                                                                    \
+    if ((rc = fv3t_##P##_set_vertical(ctx, ak, bk, ptop))) return rc;                                                          \
+    if ((rc = I->upload(FV3T_PE, pe, nq))) return rc;                                                                          \
+    if ((rc = I->upload(FV3T_Q, q, nq))) return rc;                                                                            \
+    if ((rc = I->upload(FV3T_DELP, delp, nq))) return rc;                                                                      \
+    if ((rc = I->remap_resident(nq, kord_tr, fill, 0, I->n))) return rc;                                                       \
+    if ((rc = I->download(FV3T_Q, q, nq))) return rc;                                                                          \
+    return I->download(FV3T_DELP, delp, nq);                                                                                   \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_mapn_tracer(fv3t_ctx* ctx, int nq, int km, const REAL* pe1, const REAL* pe2, REAL* q1,             \
+                                        const REAL* dp2, const int* kord, int j, int i1, int i2, int isd, int ied, int jsd,   \
+                                        int jed, REAL q_min, int fill) {                                                       \
+    NEED(ctx, P);                                                                                                              \
+    (void)pe2;                                                                                                                 \
+    (void)dp2;                                                                                                                 \
+    if (km != I->npz || i1 != 1 || i2 != I->n || isd != -2 || ied != I->n + 3 || jsd != -2 || jed != I->n + 3)                 \
+      return fail("fv3tracer: mapn_tracer bounds do not match the context (whole-tile rows only)");                           \
+    if (q_min != REAL(0)) return fail("fv3tracer: mapn_tracer is only called with q_min = 0 on this path");                   \
+    if (I->nt != 1) return fail("fv3tracer: the row-granular mapn_tracer entry needs a one-tile context");                    \
+    if (!I->have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");                          \
+    std::lock_guard<std::mutex> lk(I->row_mutex);                                                                              \
+    CK(cudaSetDevice(I->device));                                                                                              \
+    const size_t nd = I->n + 6, pl = nd * nd;                                                                                  \
+    /* pe row: pe(i1:i2, k) for this j into the (is-1:ie+1, km+1, js-1:je+1) mirror */                                         \
+    CK(cudaMemcpy2DAsync(I->pe + (size_t)j * (I->n + 2) * (km + 1) + 1, (I->n + 2) * sizeof(REAL), pe1, I->n * sizeof(REAL),   \
+                         I->n * sizeof(REAL), km + 1, cudaMemcpyHostToDevice, I->stream));                                     \
+    /* q rows: (isd:ied) of row j for every (k, iq) */                                                                         \
+    CK(cudaMemcpy2DAsync(I->q[0] + (size_t)(j + 2) * nd, pl * sizeof(REAL), q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL),      \
+                         nd * sizeof(REAL), (size_t)km * nq, cudaMemcpyHostToDevice, I->stream));                              \
+    std::fill(I->par.begin(), I->par.end(), 0);                                                                                \
+    int rc = I->remap_resident(nq, kord, fill, j - 1, 1);                                                                      \
+    if (rc) return rc;                                                                                                         \
+    CK(cudaMemcpy2DAsync(q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), I->q[0] + (size_t)(j + 2) * nd, pl * sizeof(REAL),      \
+                         nd * sizeof(REAL), (size_t)km * nq, cudaMemcpyDeviceToHost, I->stream));                              \
+    CK(cudaStreamSynchronize(I->stream));                                                                                      \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d_begin(fv3t_ctx* ctx, int nq, int q_split, REAL* cmax_local) {                            \
+    NEED(ctx, P);                                                                                                              \
+    return I->begin(nq, q_split, cmax_local);                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d_set_cmax(fv3t_ctx* ctx, const REAL* cmax_global, int q_split, int* nsplt_out) {          \
+    NEED(ctx, P);                                                                                                              \
+    return I->set_cmax(cmax_global, q_split, nsplt_out);                                                                       \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_local(fv3t_ctx* ctx, int it) {                                                                \
+    NEED(ctx, P);                                                                                                              \
+    return I->halo_local(it);                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_pack(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* dev_buf) {                        \
+    NEED(ctx, P);                                                                                                              \
+    return I->halo_pack(it, local_tile, edge, dev_buf, false);                                                                 \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_unpack(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* dev_buf) {                \
+    NEED(ctx, P);                                                                                                              \
+    return I->halo_pack(it, local_tile, edge, const_cast<REAL*>(dev_buf), true);                                               \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac) {                                 \
+    NEED(ctx, P);                                                                                                              \
+    return I->substep(it, hord, lim_fac);                                                                                      \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d_finish(fv3t_ctx* ctx) {                                                                  \
+    NEED(ctx, P);                                                                                                              \
+    return I->finish();                                                                                                        \
+  }
+
+FV3T_DEFINE(f64, double)
+FV3T_DEFINE(f32, float)
+
+#define DISPATCH(ctx, expr64, expr32) ((ctx)->prec == 8 ? (expr64) : (expr32))
+
+extern "C" int fv3t_destroy(fv3t_ctx* ctx) {
+  if (!ctx) return 0;
+  if (ctx->f64) {
+    ctx->f64->destroy();
+    delete ctx->f64;
+  }
+  if (ctx->f32) {
+    ctx->f32->destroy();
+    delete ctx->f32;
+  }
+  delete ctx;
+  return 0;
+}
+extern "C" int fv3t_sync(fv3t_ctx* ctx) {
+  if (!ctx) return fail("fv3tracer: null context");
+  cudaStream_t s = DISPATCH(ctx, ctx->f64->stream, ctx->f32->stream);
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+extern "C" void* fv3t_device_ptr(fv3t_ctx* ctx, int field) {
+  if (!ctx) return nullptr;
+  return DISPATCH(ctx, (void*)ctx->f64->field_ptr(field), (void*)ctx->f32->field_ptr(field));
+}
+extern "C" size_t fv3t_halo_strip_elems(fv3t_ctx* ctx) {
+  if (!ctx) return 0;
+  return DISPATCH(ctx, (size_t)3 * ctx->f64->n * ctx->f64->npz * ctx->f64->nq_cur, (size_t)3 * ctx->f32->n * ctx->f32->npz * ctx->f32->nq_cur);
+}
+extern "C" int fv3t_neighbor(fv3t_ctx* ctx, int global_tile, int edge, int* nbr_tile, int* nbr_edge, int* rotated) {
+  if (!ctx || global_tile < 1 || global_tile > 6 || edge < 0 || edge > 3) return fail("fv3tracer: bad tile/edge");
+  const EdgeMap& m = DISPATCH(ctx, ctx->f64->maps[global_tile - 1][edge], ctx->f32->maps[global_tile - 1][edge]);
+  if (nbr_tile) *nbr_tile = m.nbr_tile + 1;
+  if (nbr_edge) *nbr_edge = m.nbr_edge;
+  if (rotated) *rotated = (m.A[0][0] == 0);
+  return 0;
+}
+extern "C" uint64_t fv3t_kernel_launches(fv3t_ctx* ctx) {
+  if (!ctx) return 0;
+  return DISPATCH(ctx, ctx->f64->launches, ctx->f32->launches);
+}
+extern "C" int fv3t_timer_start(fv3t_ctx* ctx) {
+  if (!ctx) return fail("fv3tracer: null context");
+  if (ctx->prec == 8)
+    CK(cudaEventRecord(ctx->f64->ev0, ctx->f64->stream));
+  else
+    CK(cudaEventRecord(ctx->f32->ev0, ctx->f32->stream));
+  return 0;
+}
+extern "C" int fv3t_timer_stop_ms(fv3t_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return fail("fv3tracer: null argument");
+  cudaEvent_t e0 = DISPATCH(ctx, ctx->f64->ev0, ctx->f32->ev0), e1 = DISPATCH(ctx, ctx->f64->ev1, ctx->f32->ev1);
+  cudaStream_t s = DISPATCH(ctx, ctx->f64->stream, ctx->f32->stream);
+  CK(cudaEventRecord(e1, s));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(ms, e0, e1));
+  return 0;
+}
+extern "C" int fv3t_profile_enable(fv3t_ctx* ctx, int on) {
+  if (!ctx) return fail("fv3tracer: null context");
+  if (ctx->prec == 8) {
+    ctx->f64->prof = on != 0;
+    for (int k = 0; k < KC_N; ++k) ctx->f64->prof_ms[k] = 0, ctx->f64->prof_n[k] = 0;
+  } else {
+    ctx->f32->prof = on != 0;
+    for (int k = 0; k < KC_N; ++k) ctx->f32->prof_ms[k] = 0, ctx->f32->prof_n[k] = 0;
+  }
+  return 0;
+}
+extern "C" int fv3t_profile_get_ms(fv3t_ctx* ctx, int kc, float* total_ms, int* launches) {
+  if (!ctx || kc < 0 || kc >= KC_N) return fail("fv3tracer: bad argument");
+  if (total_ms) *total_ms = DISPATCH(ctx, ctx->f64->prof_ms[kc], ctx->f32->prof_ms[kc]);
+  if (launches) *launches = DISPATCH(ctx, ctx->f64->prof_n[kc], ctx->f32->prof_n[kc]);
+  return 0;
+}

@@ -1,0 +1,44 @@
+// fv3atm_b200: shared device helpers for the tracer-transport kernels (sm_100a).
+//
+// Arithmetic contract: every expression in the kernels keeps the operation order of the reference
+// Fortran (atmos_cubed_sphere/model/tp_core.F90, fv_tracer2d.F90, fv_mapz.F90, fv_fill.F90).  Built with
+// -fmad=false and IEEE division the fp64/fp32 results are bit-identical to an FMA-free CPU evaluation.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fv3t {
+
+constexpr int NG = 3;  // halo width (fv_mp_mod.F90:104)
+
+// Fortran SIGN(a,b): |a| with the sign bit of b (tp_core.F90:565)
+__device__ __forceinline__ double f_sign(double a, double b) { return copysign(a, b); }
+__device__ __forceinline__ float f_sign(float a, float b) { return copysignf(a, b); }
+__device__ __forceinline__ double f_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float f_abs(float a) { return fabsf(a); }
+// Fortran MAX/MIN on non-NaN data
+template <class T> __device__ __forceinline__ T f_max(T a, T b) { return a > b ? a : b; }
+template <class T> __device__ __forceinline__ T f_min(T a, T b) { return a < b ? a : b; }
+template <class T> __device__ __forceinline__ T f_max(T a, T b, T c) { return f_max(f_max(a, b), c); }
+template <class T> __device__ __forceinline__ T f_min(T a, T b, T c) { return f_min(f_min(a, b), c); }
+template <class T> __device__ __forceinline__ T f_max(T a, T b, T c, T d) { return f_max(f_max(f_max(a, b), c), d); }
+template <class T> __device__ __forceinline__ T f_min(T a, T b, T c, T d) { return f_min(f_min(f_min(a, b), c), d); }
+
+// default-real literal constants of tp_core.F90:62-98 and fv_mapz.F90:110, folded at compile time in T
+template <class T> struct K {
+  static __device__ __forceinline__ constexpr T r3() { return T(1) / T(3); }
+  static __device__ __forceinline__ constexpr T r23() { return T(2) / T(3); }
+  static __device__ __forceinline__ constexpr T r12() { return T(1) / T(12); }
+  static __device__ __forceinline__ constexpr T near_zero() { return T(1.0e-25); }
+  static __device__ __forceinline__ constexpr T ppm_fac() { return T(1.5); }
+  static __device__ __forceinline__ constexpr T s11() { return T(11) / T(14); }
+  static __device__ __forceinline__ constexpr T s14() { return T(4) / T(7); }
+  static __device__ __forceinline__ constexpr T s15() { return T(3) / T(14); }
+  static __device__ __forceinline__ constexpr T c1() { return T(-2) / T(14); }
+  static __device__ __forceinline__ constexpr T c2() { return T(11) / T(14); }
+  static __device__ __forceinline__ constexpr T c3() { return T(5) / T(14); }
+  static __device__ __forceinline__ constexpr T p1() { return T(7) / T(12); }
+  static __device__ __forceinline__ constexpr T p2() { return T(-1) / T(12); }
+};
+
+}  // namespace fv3t

@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference interface for the tracer-transport path, on top of the C-ABI.
+
+Names and argument meaning follow the reference (atmos_cubed_sphere/model/fv_tracer2d.F90:324 tracer_2d,
+model/fv_mapz.F90:134 Lagrangian_to_Eulerian (tracer part), :1386 mapn_tracer); arrays use the package
+convention: numpy C-order with the reversed Fortran shape and a leading tile axis, i.e. exactly the bytes
+of the tile-major stack of Fortran arrays the C-ABI takes.  All compute happens in libfv3tracer.so on the
+GPU; nothing here falls back to the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import lib as L
+
+
+class TracerContext:
+    """Device-resident state of the path for `ntiles` cubed-sphere tiles on one GPU (fv3t_ctx)."""
+
+    def __init__(self, npx: int, npz: int, nq_max: int, grid: dict, dtype=np.float64, tiles=(1, 2, 3, 4, 5, 6),
+                 device: int = 0, stream: int | None = None):
+        self.dtype = np.dtype(dtype)
+        self.npx, self.npz, self.nq_max = int(npx), int(npz), int(nq_max)
+        self.n = self.npx - 1
+        self.tiles = tuple(int(t) for t in tiles)
+        self.nt = len(self.tiles)
+        d = L.Dims(self.npx, self.npz, self.nq_max, self.nt, (C.c_int * 6)(*(list(self.tiles) + [0] * (6 - self.nt))))
+        g = L.GridPtrs()
+        self._keep = []
+        for k in ("area", "rarea", "dx", "dy", "dxa", "dya", "sin_sg"):
+            a = np.ascontiguousarray(grid[k], dtype=self.dtype)
+            if a.shape[0] != self.nt:
+                a = np.ascontiguousarray(a[[t - 1 for t in self.tiles]])
+            self._keep.append(a)
+            setattr(g, k, a.ctypes.data)
+        self._h = C.c_void_p()
+        L.check(L.fn(self.dtype, "create")(C.byref(self._h), C.byref(d), C.byref(g), int(device),
+                                           C.c_void_p(stream) if stream else None))
+        self._ct = L.prec(self.dtype)[1]
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            L.load().fv3t_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _f(self, name):
+        return L.fn(self.dtype, name)
+
+    # ---- reference-facing host-array entry points -------------------------------------------------
+    def tracer_2d(self, q, dp1, mfx, mfy, cx, cy, hord, q_split=0, nord_tr=0, trdm=0.0, lim_fac=1.0):
+        """tracer_2d(q, dp1, mfx, mfy, cx, cy, ..., nq, hord, q_split, ..., nord_tr, trdm, lim_fac): in-place on the
+        numpy arrays like the Fortran INTENT(INOUT) dummies.  Returns (nsplt, ksplt)."""
+        nq = q.shape[1]
+        for a in (q, dp1, mfx, mfy, cx, cy):
+            assert a.dtype == self.dtype and a.flags["C_CONTIGUOUS"]
+        nsplt = C.c_int(0)
+        ksplt = np.zeros(self.npz, dtype=np.int32)
+        L.check(self._f("tracer_2d")(self._h, L.ptr(q), L.ptr(dp1), L.ptr(mfx), L.ptr(mfy), L.ptr(cx), L.ptr(cy), int(nq),
+                                     int(hord), int(q_split), int(nord_tr), self._ct(trdm), self._ct(lim_fac),
+                                     C.byref(nsplt), L.ptr(ksplt)))
+        return nsplt.value, ksplt
+
+    def remap_tracers(self, pe, ak, bk, ptop, q, delp, kord_tr, fill=True):
+        """Tracer part of Lagrangian_to_Eulerian for every row: q and delp updated in place."""
+        nq = q.shape[1]
+        kord = np.ascontiguousarray(np.broadcast_to(np.asarray(kord_tr, dtype=np.int32), (nq,)))
+        ak = np.ascontiguousarray(ak, dtype=self.dtype)
+        bk = np.ascontiguousarray(bk, dtype=self.dtype)
+        L.check(self._f("remap_tracers")(self._h, L.ptr(pe), L.ptr(ak), L.ptr(bk), self._ct(ptop), L.ptr(q), L.ptr(delp),
+                                         int(nq), L.ptr(kord), int(bool(fill))))
+
+    def mapn_tracer(self, nq, km, pe1, pe2, q1, dp2, kord, j, i1, i2, isd, ied, jsd, jed, q_min, fill):
+        """Row-granular entry with the reference's own argument list (one-tile context)."""
+        kord = np.ascontiguousarray(kord, dtype=np.int32)
+        L.check(self._f("mapn_tracer")(self._h, int(nq), int(km), L.ptr(pe1), L.ptr(pe2), L.ptr(q1), L.ptr(dp2), L.ptr(kord),
+                                       int(j), int(i1), int(i2), int(isd), int(ied), int(jsd), int(jed), self._ct(q_min),
+                                       int(bool(fill))))
+
+    # ---- device-resident operation -------------------------------------------------------------------
+    def upload(self, field: str, host: np.ndarray, nq: int | None = None):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        L.check(self._f("upload")(self._h, L.FIELD[field], L.ptr(host), int(nq if nq is not None else self.nq_max)))
+        self.sync()
+
+    def upload_ptr(self, field: str, host_ptr: int, nq: int):
+        """Asynchronous upload from (pinned) host memory given by address."""
+        L.check(self._f("upload")(self._h, L.FIELD[field], C.c_void_p(host_ptr), int(nq)))
+
+    def download(self, field: str, host: np.ndarray, nq: int | None = None):
+        assert host.dtype == self.dtype and host.flags["C_CONTIGUOUS"]
+        L.check(self._f("download")(self._h, L.FIELD[field], L.ptr(host), int(nq if nq is not None else self.nq_max)))
+        return host
+
+    def download_ptr(self, field: str, host_ptr: int, nq: int):
+        L.check(self._f("download")(self._h, L.FIELD[field], C.c_void_p(host_ptr), int(nq)))
+
+    def set_vertical(self, ak, bk, ptop):
+        ak = np.ascontiguousarray(ak, dtype=self.dtype)
+        bk = np.ascontiguousarray(bk, dtype=self.dtype)
+        L.check(self._f("set_vertical")(self._h, L.ptr(ak), L.ptr(bk), self._ct(ptop)))
+
+    def tracer_2d_resident(self, nq, hord, q_split=0, lim_fac=1.0) -> int:
+        nsplt = C.c_int(0)
+        L.check(self._f("tracer_2d_resident")(self._h, int(nq), int(hord), int(q_split), self._ct(lim_fac), C.byref(nsplt)))
+        return nsplt.value
+
+    def remap_tracers_resident(self, nq, kord_tr, fill=True):
+        kord = np.ascontiguousarray(np.broadcast_to(np.asarray(kord_tr, dtype=np.int32), (nq,)))
+        L.check(self._f("remap_tracers_resident")(self._h, int(nq), L.ptr(kord), int(bool(fill))))
+
+    # ---- building blocks for face-sharded contexts ---------------------------------------------------
+    def tracer_2d_begin(self, nq, q_split=0):
+        cmax = np.zeros(self.npz, dtype=self.dtype)
+        L.check(self._f("tracer_2d_begin")(self._h, int(nq), int(q_split), L.ptr(cmax)))
+        return cmax
+
+    def tracer_2d_set_cmax(self, cmax, q_split=0) -> int:
+        cmax = np.ascontiguousarray(cmax, dtype=self.dtype)
+        nsplt = C.c_int(0)
+        L.check(self._f("tracer_2d_set_cmax")(self._h, L.ptr(cmax), int(q_split), C.byref(nsplt)))
+        return nsplt.value
+
+    def halo_local(self, it):
+        L.check(self._f("halo_local")(self._h, int(it)))
+
+    def halo_pack(self, it, local_tile, edge, dev_ptr):
+        L.check(self._f("halo_pack")(self._h, int(it), int(local_tile), int(edge), C.c_void_p(dev_ptr)))
+
+    def halo_unpack(self, it, local_tile, edge, dev_ptr):
+        L.check(self._f("halo_unpack")(self._h, int(it), int(local_tile), int(edge), C.c_void_p(dev_ptr)))
+
+    def tracer_2d_substep(self, it, hord, lim_fac=1.0):
+        L.check(self._f("tracer_2d_substep")(self._h, int(it), int(hord), self._ct(lim_fac)))
+
+    def tracer_2d_finish(self):
+        L.check(self._f("tracer_2d_finish")(self._h))
+
+    # ---- misc
+    def sync(self):
+        L.check(L.load().fv3t_sync(self._h))
+
+    def device_ptr(self, field: str) -> int:
+        return int(L.load().fv3t_device_ptr(self._h, L.FIELD[field]) or 0)
+
+    def halo_strip_elems(self) -> int:
+        return int(L.load().fv3t_halo_strip_elems(self._h))
+
+    def neighbor(self, global_tile: int, edge: int):
+        t, e, r = C.c_int(), C.c_int(), C.c_int()
+        L.check(L.load().fv3t_neighbor(self._h, int(global_tile), int(edge), C.byref(t), C.byref(e), C.byref(r)))
+        return t.value, e.value, bool(r.value)
+
+    def kernel_launches(self) -> int:
+        return int(L.load().fv3t_kernel_launches(self._h))
+
+    def timer_start(self):
+        L.check(L.load().fv3t_timer_start(self._h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        L.check(L.load().fv3t_timer_stop_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def profile_enable(self, on=True):
+        L.check(L.load().fv3t_profile_enable(self._h, int(bool(on))))
+
+    def profile_get(self, kclass: str):
+        ms, nl = C.c_float(), C.c_int()
+        L.check(L.load().fv3t_profile_get_ms(self._h, L.KCLASS[kclass], C.byref(ms), C.byref(nl)))
+        return float(ms.value), int(nl.value)

@@ -1,0 +1,144 @@
+/* fv3tracer.h -- C-ABI of the B200-native FV3 tracer-transport path (libfv3tracer.so).
+ *
+ * Drop-in boundary for ONE hot path of NOAA-EMC/fv3atm (submodule atmos_cubed_sphere, "ACS/"):
+ *   - sub-cycled horizontal tracer advection   ACS/model/fv_tracer2d.F90:324-569 (tracer_2d; tracer_2d_1L :92-321 is
+ *     numerically identical for q_split = 0, trdm2 = 0) -> ACS/model/tp_core.F90:110-249 (fv_tp_2d), xppm/yppm/
+ *     copy_corners/pert_ppm (:253-1236)
+ *   - vertical Lagrangian-to-Eulerian tracer remap  ACS/model/fv_mapz.F90:261-273,343-368,407-426 (tracer part of
+ *     Lagrangian_to_Eulerian) -> mapn_tracer (:1386-1499) / map1_q2 (:1502-1592), scalar_profile (:1691-2096),
+ *     cs_limiters (:2501-2576), ppm_profile/ppm_limiters (:2580-2916), fillz (ACS/model/fv_fill.F90:51-156)
+ *
+ * Conventions
+ *   - Plain C: raw pointers + sizes.  Every array has EXACTLY the Fortran layout of the reference's dummy argument
+ *     (column-major, i contiguous) with the global-domain bounds is=js=1, ie=je=npx-1, ng=3:
+ *         q   (isd:ied, jsd:jed, npz, nq)      dp1, delp (isd:ied, jsd:jed, npz)
+ *         cx  (is:ie+1, jsd:jed, npz)          cy  (isd:ied, js:je+1, npz)
+ *         mfx (is:ie+1, js:je,  npz)           mfy (is:ie,  js:je+1, npz)
+ *         pe  (is-1:ie+1, npz+1, js-1:je+1)    ak, bk (npz+1)
+ *     A context holds `ntiles` cubed-sphere tiles (all six for a whole mosaic on one GPU); multi-tile arguments are
+ *     the per-tile Fortran arrays stacked tile-major (tile stride = size of one tile's array).
+ *   - Two symbol sets, fv3t_f64_* and fv3t_f32_*, mirror the reference's 64-bit and 32-bit (-D32BIT) dycore builds
+ *     (ACS/CMakeLists.txt:27); declared below by the FV3T_DECLARE macro with REAL = double / float.
+ *   - All functions return 0 on success, non-zero on error (fv3t_last_error() gives the message).  The reference has
+ *     no status returns (mpp_error(FATAL) aborts, fv_tracer2d.F90:76); the Fortran shim maps non-zero to that.
+ *   - `stream` arguments are cudaStream_t passed as void* (NULL = default stream).  Host-array entry points are
+ *     synchronous; *_resident entry points only enqueue work on the context's stream.
+ *   - There is no CPU fallback: creating a context without a CUDA device fails.
+ */
+#ifndef FV3TRACER_H
+#define FV3TRACER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fv3t_ctx fv3t_ctx;
+
+/* fv_grid_bounds_type + the scalar members the path needs (ACS/model/fv_arrays.F90:1178-1186, :181-208) */
+typedef struct fv3t_dims {
+  int npx;        /* cells per tile edge + 1 (npx == npy on the cubed sphere)                   */
+  int npz;        /* number of levels (<= 128 in this build)                                      */
+  int nq_max;     /* capacity: largest nq any call will pass                                     */
+  int ntiles;     /* tiles resident in this context, 1..6                                        */
+  int tile_id[6]; /* global tile numbers (1..6) of the resident tiles, in storage order          */
+} fv3t_dims;
+
+/* Device-resident fields addressable through fv3t_*_upload/download/device_ptr */
+enum fv3t_field {
+  FV3T_Q = 0,   /* tracers; after tracer_2d a level may live in either ping-pong buffer: download gathers    */
+  FV3T_DP1 = 1, /* delp before dyn_core (updated in place between sub-steps, fv_tracer2d.F90:547-553)        */
+  FV3T_MFX = 2,
+  FV3T_MFY = 3,
+  FV3T_CX = 4,
+  FV3T_CY = 5,
+  FV3T_PE = 6,  /* Lagrangian interface pressure, (i,k,j) order                                              */
+  FV3T_DELP = 7 /* Eulerian delp written by the remap (fv_mapz.F90:364-368)                                   */
+};
+
+const char* fv3t_last_error(void);
+int fv3t_device_count(void);
+
+#define FV3T_DECLARE(P, REAL)                                                                                           \
+  /* The fv_grid_type members the path reads (ACS/model/fv_arrays.F90:81-88,157): `real` copies, tile-major,         \
+     extents area/rarea/dxa/dya (isd:ied,jsd:jed), dx (isd:ied,jsd:jed+1), dy (isd:ied+1,jsd:jed),                     \
+     sin_sg (isd:ied,jsd:jed,5) = sub-cell positions 1..5 of sin_sg(:,:,9).  Replaces gridstruct in the                \
+     reference's tracer_2d / fv_tp_2d argument lists. */                                                               \
+  typedef struct fv3t_##P##_grid {                                                                                      \
+    const REAL *area, *rarea, *dx, *dy, *dxa, *dya, *sin_sg;                                                            \
+  } fv3t_##P##_grid;                                                                                                    \
+                                                                                                                        \
+  /* Allocate device mirrors and upload the grid.  Replaces nothing in the reference (state is Fortran-owned there);   \
+     corresponds to the lifetime of fv_atmos_type (fv_arrays.F90:1386). */                                             \
+  int fv3t_##P##_create(fv3t_ctx** ctx, const fv3t_dims* dims, const fv3t_##P##_grid* grid, int device, void* stream);  \
+                                                                                                                        \
+  /* tracer_2d(q, dp1, mfx, mfy, cx, cy, gridstruct, bd, domain, npx, npy, npz, nq, hord, q_split, dt, id_divg,        \
+               q_pack, dp1_pack, nord_tr, trdm, lim_fac)            ACS/model/fv_tracer2d.F90:324-345                  \
+     Host arrays in, host arrays out; reproduces the reference's side effects: q updated on the compute domain,       \
+     cx, cy, mfx, mfy scaled by 1/ksplt(k) when nsplt /= 1 (:463-481), dp1 advanced between sub-steps (:549).         \
+     The halo update of q that the reference completes at :499 is performed internally for the resident tiles          \
+     (requires ntiles == 6).  nord_tr/trdm: only trdm <= 1e-4 (no tracer damping) is supported -> error otherwise.     \
+     nsplt_out / ksplt_out[npz] (optional) return the sub-step counts (:441,:457). */                                  \
+  int fv3t_##P##_tracer_2d(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,         \
+                           int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out, int* ksplt_out); \
+                                                                                                                        \
+  /* Tracer part of Lagrangian_to_Eulerian for all rows js..je at once (the j loop of fv_mapz.F90:261 hoisted):        \
+     pe1 = pe(:,:,j); pe2 = ak + bk*pe(:,km+1,j); dp2; delp <- dp2 (:263-272,350-368); then mapn_tracer (nq > 5) or   \
+     map1_q2 + fillz per tracer (:410-426).  q and delp are updated in place on the compute domain. */                 \
+  int fv3t_##P##_remap_tracers(fv3t_ctx* ctx, const REAL* pe, const REAL* ak, const REAL* bk, REAL ptop, REAL* q,       \
+                               REAL* delp, int nq, const int* kord_tr, int fill);                                       \
+                                                                                                                        \
+  /* mapn_tracer(nq, km, pe1, pe2, q1, dp2, kord, j, i1, i2, isd, ied, jsd, jed, q_min, fill)   fv_mapz.F90:1386-1402  \
+     Row-granular compatibility entry with the reference's own argument list (one tile, one row j; pe1, pe2           \
+     (i1:i2, km+1), dp2 (i1:i2, km), q1 (isd:ied, jsd:jed, km, nq)).  Thread-safe (the reference calls it from an      \
+     OpenMP loop over j, fv_mapz.F90:250-261); serialised internally.  Prefer fv3t_*_remap_tracers. */                 \
+  int fv3t_##P##_mapn_tracer(fv3t_ctx* ctx, int nq, int km, const REAL* pe1, const REAL* pe2, REAL* q1, const REAL* dp2, \
+                             const int* kord, int j, int i1, int i2, int isd, int ied, int jsd, int jed, REAL q_min,   \
+                             int fill);                                                                                 \
+                                                                                                                        \
+  /* Device-resident operation (north star: tracers, Courant numbers, mass fluxes and delp stay in HBM). */            \
+  int fv3t_##P##_upload(fv3t_ctx* ctx, int field, const REAL* host, int nq);                                            \
+  int fv3t_##P##_download(fv3t_ctx* ctx, int field, REAL* host, int nq);                                                \
+  int fv3t_##P##_set_vertical(fv3t_ctx* ctx, const REAL* ak, const REAL* bk, REAL ptop);                                \
+  int fv3t_##P##_tracer_2d_resident(fv3t_ctx* ctx, int nq, int hord, int q_split, REAL lim_fac, int* nsplt_out);        \
+  int fv3t_##P##_remap_tracers_resident(fv3t_ctx* ctx, int nq, const int* kord_tr, int fill);                           \
+                                                                                                                        \
+  /* Building blocks for a context that holds only some tiles (face sharding): the caller transports the packed       \
+     edge strips between contexts (NCCL send/recv in this repo, MPI in a Fortran host) and reduces cmax.               \
+       begin   : steps A-B of tracer_2d up to the local cmax(1:npz) (fv_tracer2d.F90:387-427), returned on the host    \
+       set_cmax: the globally reduced cmax -> nsplt, ksplt(k) (:432-457)                                                \
+       halo_pack / halo_unpack: pack the 3-cell edge strips each remote neighbour needs, already rotated into the      \
+                 receiver's index order (mosaic contacts, ACS/tools/fv_mp_mod.F90:581-629) / scatter received strips  \
+       substep : one pass of the `it` loop body (:503-556) for the resident tiles                                     \
+       finish  : the in-place 1/ksplt scaling of cx, cy, mfx, mfy (:463-481) */                                        \
+  int fv3t_##P##_tracer_2d_begin(fv3t_ctx* ctx, int nq, int q_split, REAL* cmax_local);                                 \
+  int fv3t_##P##_tracer_2d_set_cmax(fv3t_ctx* ctx, const REAL* cmax_global, int q_split, int* nsplt_out);               \
+  int fv3t_##P##_halo_local(fv3t_ctx* ctx, int it);                                                                     \
+  int fv3t_##P##_halo_pack(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* dev_buf);                             \
+  int fv3t_##P##_halo_unpack(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* dev_buf);                     \
+  int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac);                                      \
+  int fv3t_##P##_tracer_2d_finish(fv3t_ctx* ctx);
+
+FV3T_DECLARE(f64, double)
+FV3T_DECLARE(f32, float)
+
+/* Precision-independent calls */
+int fv3t_destroy(fv3t_ctx* ctx);
+int fv3t_sync(fv3t_ctx* ctx);
+void* fv3t_device_ptr(fv3t_ctx* ctx, int field); /* base of the device mirror (FV3T_Q: buffer 0)             */
+size_t fv3t_halo_strip_elems(fv3t_ctx* ctx);     /* elements of one packed edge strip: 3*(npx-1)*npz*nq_cur  */
+int fv3t_neighbor(fv3t_ctx* ctx, int global_tile, int edge, int* nbr_tile, int* nbr_edge, int* rotated);
+uint64_t fv3t_kernel_launches(fv3t_ctx* ctx);    /* kernels launched by this context so far (bench accounting) */
+/* CUDA-event timing of the kernels enqueued between the two calls on the context's stream */
+int fv3t_timer_start(fv3t_ctx* ctx);
+int fv3t_timer_stop_ms(fv3t_ctx* ctx, float* ms);
+/* per-kernel-class accumulated device time since the last reset: 0 advect, 1 remap, 2 halo, 3 cmax, 4 scale    */
+int fv3t_profile_enable(fv3t_ctx* ctx, int on);
+int fv3t_profile_get_ms(fv3t_ctx* ctx, int kernel_class, float* total_ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FV3TRACER_H */
