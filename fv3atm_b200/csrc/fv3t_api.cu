@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,6 +17,7 @@
 #include "../../include/fv3tracer.h"
 #include "fv3t_advect.cuh"
 #include "fv3t_remap.cuh"
+#include "fv3t_remap2.cuh"
 
 namespace {
 
@@ -124,14 +126,15 @@ template <class T> struct Impl {
   T *area = nullptr, *rarea = nullptr, *dx = nullptr, *dy = nullptr, *dxa = nullptr, *dya = nullptr, *sin_sg = nullptr;
   T *ak = nullptr, *bk = nullptr, *cmax_t = nullptr;
   T ptop = T(0);
-  int *ksplt_d = nullptr, *par_d = nullptr, *kord_d = nullptr, *halo_dst = nullptr, *halo_src = nullptr;
+  int *ksplt_d = nullptr, *par_d = nullptr, *cpy_d = nullptr, *kord_d = nullptr, *halo_dst = nullptr, *halo_src = nullptr;
+  int cur = 0;  // outside tracer_2d every level of q lives in q[cur]; sub-step `it` reads q[(cur+it-1)&1] and writes the other
   int halo_len = 0;
   int* strip_idx[6][4] = {};  // per local tile / edge: device index lists (3n) for pack (src cells) and unpack (halo cells)
   int* strip_halo[6][4] = {};
   EdgeMap maps[6][4];
   int local_of[6];  // global tile (0-based) -> local slot or -1
   // host state
-  std::vector<int> ksplt, par;
+  std::vector<int> ksplt, cpy;
   std::vector<T> cmax_h;
   int nsplt = 1, nq_cur = 0;
   bool have_vertical = false;
@@ -166,7 +169,7 @@ template <class T> struct Impl {
   }
   T* field_ptr(int f) {
     switch (f) {
-      case FV3T_Q: return q[0];
+      case FV3T_Q: return q[cur];
       case FV3T_DP1: return dp1;
       case FV3T_MFX: return mfx;
       case FV3T_MFY: return mfy;
@@ -261,10 +264,11 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   CK(dalloc(&cmax_t, (size_t)nt * npz));
   CK(cudaMalloc((void**)&ksplt_d, npz * sizeof(int)));
   CK(cudaMalloc((void**)&par_d, npz * sizeof(int)));
+  CK(cudaMalloc((void**)&cpy_d, npz * sizeof(int)));
   CK(cudaMalloc((void**)&kord_d, nqmax * sizeof(int)));
   CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
   ksplt.assign(npz, 1);
-  par.assign(npz, 0);
+  cpy.assign(npz, 0);
   cmax_h.assign((size_t)nt * npz, T(0));
 
   // halo tables: local gathers (both tiles resident) + per-edge strips for remote exchange
@@ -320,7 +324,7 @@ template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
   void* ptrs[] = {q[0], q[1], dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
-                  ksplt_d, par_d, kord_d, halo_dst, halo_src, row_buf};
+                  ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int s = 0; s < 6; ++s)
@@ -342,11 +346,7 @@ template <class T> int Impl<T>::upload(int f, const T* h, int nq) {
   if (f == FV3T_Q && (nq < 1 || nq > nqmax)) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
   CK(cudaSetDevice(device));
   CK(cudaMemcpyAsync(dptr, h, field_elems(f, nq) * sizeof(T), cudaMemcpyHostToDevice, stream));
-  if (f == FV3T_Q) {
-    nq_cur = nq;
-    std::fill(par.begin(), par.end(), 0);
-    CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
-  }
+  if (f == FV3T_Q) nq_cur = nq;
   return 0;
 }
 
@@ -354,25 +354,8 @@ template <class T> int Impl<T>::download(int f, T* h, int nq) {
   T* dptr = field_ptr(f);
   if (!dptr) return fail("fv3tracer: unknown field %d", f);
   CK(cudaSetDevice(device));
-  if (f != FV3T_Q) {
-    CK(cudaMemcpyAsync(h, dptr, field_elems(f, nq) * sizeof(T), cudaMemcpyDeviceToHost, stream));
-  } else {
-    if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
-    // gather every level from the ping-pong buffer it currently lives in
-    const size_t pl = plane();
-    bool any = false;
-    for (int k = 0; k < npz; ++k) any |= par[k] != 0;
-    if (!any) {
-      CK(cudaMemcpyAsync(h, q[0], sz_q(nq) * nt * sizeof(T), cudaMemcpyDeviceToHost, stream));
-    } else {
-      for (int t = 0; t < nt; ++t)
-        for (int iq = 0; iq < nq; ++iq)
-          for (int k = 0; k < npz; ++k) {
-            const size_t off = (((size_t)t * nq + iq) * npz + k) * pl;
-            CK(cudaMemcpyAsync(h + off, q[par[k]] + off, pl * sizeof(T), cudaMemcpyDeviceToHost, stream));
-          }
-    }
-  }
+  if (f == FV3T_Q && (nq < 1 || nq > nqmax)) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  CK(cudaMemcpyAsync(h, dptr, field_elems(f, nq) * sizeof(T), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   return 0;
 }
@@ -382,20 +365,6 @@ template <class T> int Impl<T>::begin(int nq, int q_split, T* cmax_local) {
   if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
   CK(cudaSetDevice(device));
   nq_cur = nq;
-  // a previous tracer_2d without a remap may have left levels in buffer 1
-  bool any = false;
-  for (int k = 0; k < npz; ++k) any |= par[k] != 0;
-  if (any) {
-    for (int t = 0; t < nt; ++t) {
-      const long total = (long)sz_q(nq);
-      kbegin();
-      fv3t::k_copy_levels<T><<<1184, 256, 0, stream>>>(q[0] + (size_t)t * total, q[1] + (size_t)t * total, par_d, (long)plane(), npz,
-                                                       total);
-      kend(KC_SCALE);
-    }
-    std::fill(par.begin(), par.end(), 0);
-    CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
-  }
   if (q_split == 0) {
     kbegin();
     fv3t::k_cmax<T><<<nt * npz, 512, 0, stream>>>(cx, cy, sin_sg, cmax_t, n, npz);
@@ -442,7 +411,7 @@ template <class T> int Impl<T>::halo_local(int it) {
   CK(cudaSetDevice(device));
   dim3 grid((halo_len + 255) / 256, nq_cur * npz);
   kbegin();
-  fv3t::k_halo_fill<T><<<grid, 256, 0, stream>>>(q[(it - 1) & 1], halo_dst, halo_src, halo_len, n, npz, nq_cur, ksplt_d, it);
+  fv3t::k_halo_fill<T><<<grid, 256, 0, stream>>>(q[(cur + it - 1) & 1], halo_dst, halo_src, halo_len, n, npz, nq_cur, ksplt_d, it);
   kend(KC_HALO);
   CK(cudaGetLastError());
   return 0;
@@ -467,7 +436,7 @@ template <class T> int Impl<T>::halo_pack(int it, int lt, int edge, T* buf, bool
   if (lt < 0 || lt >= nt || edge < 0 || edge > 3) return fail("fv3tracer: bad tile/edge %d/%d", lt, edge);
   CK(cudaSetDevice(device));
   dim3 grid((3 * n + 255) / 256, nq_cur * npz);
-  T* qt = q[(it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
+  T* qt = q[(cur + it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
   kbegin();
   k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, unpack ? strip_halo[lt][edge] : strip_idx[lt][edge], n, npz, nq_cur, ksplt_d, it,
                                        unpack ? 1 : 0);
@@ -498,8 +467,8 @@ template <class T, int OI, int OO> int launch_advect(Impl<T>& c, const fv3t::Adv
 template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   CK(cudaSetDevice(device));
   fv3t::AdvParams<T> p;
-  p.qin = q[(it - 1) & 1];
-  p.qout = q[it & 1];
+  p.qin = q[(cur + it - 1) & 1];
+  p.qout = q[(cur + it) & 1];
   p.dp1 = dp1;
   p.mfx = mfx;
   p.mfy = mfy;
@@ -532,15 +501,32 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     case 4: rc = launch_advect<T, 4, 4>(*this, p); break;
     default: return fail("fv3tracer: hord_tr = %d is not a scheme of xppm/yppm", hord);
   }
-  if (rc) return rc;
-  for (int k = 0; k < npz; ++k)
-    if (it <= ksplt[k]) par[k] = it & 1;
-  return 0;
+  return rc;
 }
 
 template <class T> int Impl<T>::finish() {
   CK(cudaSetDevice(device));
-  CK(cudaMemcpyAsync(par_d, par.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
+  // level k has been advanced ksplt(k) times and lives in q[(cur + ksplt(k)) & 1]; gather every level in q[(cur + nsplt) & 1]
+  const int fin = (cur + nsplt) & 1;
+  if (nsplt != 1) {
+    bool any = false;
+    for (int k = 0; k < npz; ++k) {
+      cpy[k] = (ksplt[k] ^ nsplt) & 1;
+      any |= cpy[k] != 0;
+    }
+    if (any) {
+      CK(cudaMemcpyAsync(cpy_d, cpy.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));  // cpy is reused by the next call
+      for (int t = 0; t < nt; ++t) {
+        const long total = (long)sz_q(nq_cur);
+        kbegin();
+        fv3t::k_copy_levels<T><<<1184, 256, 0, stream>>>(q[fin] + (size_t)t * total, q[fin ^ 1] + (size_t)t * total, cpy_d, (long)plane(),
+                                                         npz, total);
+        kend(KC_SCALE);
+      }
+    }
+  }
+  cur = fin;
   if (nsplt != 1) {
     struct A {
       T* p;
@@ -576,43 +562,86 @@ template <class T> int Impl<T>::tracer_2d_resident(int nq, int hord, int q_split
   return finish();
 }
 
+template <class T, int G, bool MAPN> int launch_remap2(Impl<T>& c, const fv3t::Remap2Params<T>& p) {
+  const int cols = c.n * p.j_count;
+  dim3 grid((cols + 127) / 128, c.nt, (p.nq + G - 1) / G);
+  c.kbegin();
+  if (c.npz <= 64)
+    fv3t::k_remap2<T, G, MAPN, 64><<<grid, 128, 0, c.stream>>>(p);
+  else
+    fv3t::k_remap2<T, G, MAPN, 128><<<grid, 128, 0, c.stream>>>(p);
+  c.kend(KC_REMAP);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Tracer part of Lagrangian_to_Eulerian for rows js+j_first .. (fv_mapz.F90:261-273, 343-368, 407-426): reads q[cur],
+// writes q[cur^1]; a whole-tile call (j_count == n) makes the written buffer the current one.
 template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill, int j_first, int j_count) {
   if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
   if (!have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
   CK(cudaSetDevice(device));
   CK(cudaMemcpyAsync(kord_d, kord, nq * sizeof(int), cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(par_d, par.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
-  fv3t::RemapParams<T> p;
-  p.q0 = q[0];
-  p.q1 = q[1];
-  p.qout = q[0];
-  p.par = par_d;
-  p.pe = pe;
-  p.ak = ak;
-  p.bk = bk;
-  p.delp = delp;
-  p.kord = kord_d;
-  p.ptop = ptop;
-  p.n = n;
-  p.km = npz;
-  p.nq = nq;
-  p.ntiles = nt;
-  p.fill = fill;
-  p.j_first = j_first;
-  p.j_count = j_count;
-  const int cols = n * j_count;
-  dim3 grid((cols + 63) / 64, nt);
-  kbegin();
-  if (npz <= 64)
-    fv3t::k_remap<T, 64><<<grid, 64, 0, stream>>>(p);
-  else
-    fv3t::k_remap<T, 128><<<grid, 64, 0, stream>>>(p);
-  kend(KC_REMAP);
-  CK(cudaGetLastError());
-  if (j_count == n) {
-    std::fill(par.begin(), par.end(), 0);
-    CK(cudaMemsetAsync(par_d, 0, npz * sizeof(int), stream));
+  const bool mapn = nq > 5;  // fv_mapz.F90:410: mapn_tracer for nq > 5, else map1_q2 + fillz per tracer
+  bool need_ppm = false;     // map1_q2 sends kord <= 7 to ppm_profile (fv_mapz.F90:1544-1548)
+  if (!mapn)
+    for (int iq = 0; iq < nq; ++iq) need_ppm |= kord[iq] <= 7;
+  int rc = 0;
+  if (need_ppm) {
+    fv3t::RemapParams<T> p;
+    p.q0 = q[cur];
+    p.q1 = q[cur];
+    p.qout = q[cur ^ 1];
+    p.par = par_d;  // all zero
+    p.pe = pe;
+    p.ak = ak;
+    p.bk = bk;
+    p.delp = delp;
+    p.kord = kord_d;
+    p.ptop = ptop;
+    p.n = n;
+    p.km = npz;
+    p.nq = nq;
+    p.ntiles = nt;
+    p.fill = fill;
+    p.j_first = j_first;
+    p.j_count = j_count;
+    const int cols = n * j_count;
+    dim3 grid((cols + 63) / 64, nt);
+    kbegin();
+    if (npz <= 64)
+      fv3t::k_remap<T, 64><<<grid, 64, 0, stream>>>(p);
+    else
+      fv3t::k_remap<T, 128><<<grid, 64, 0, stream>>>(p);
+    kend(KC_REMAP);
+    CK(cudaGetLastError());
+  } else {
+    fv3t::Remap2Params<T> p;
+    p.qsrc = q[cur];
+    p.qdst = q[cur ^ 1];
+    p.pe = pe;
+    p.ak = ak;
+    p.bk = bk;
+    p.delp = delp;
+    p.kord = kord_d;
+    p.ptop = ptop;
+    p.n = n;
+    p.km = npz;
+    p.nq = nq;
+    p.ntiles = nt;
+    p.fill = fill;
+    p.j_first = j_first;
+    p.j_count = j_count;
+    static const int gsel = getenv("FV3T_REMAP_G") ? atoi(getenv("FV3T_REMAP_G")) : 1;  // tuning knob (tracers per thread)
+    if (gsel == 1)
+      rc = mapn ? launch_remap2<T, 1, true>(*this, p) : launch_remap2<T, 1, false>(*this, p);
+    else if (gsel == 2)
+      rc = mapn ? launch_remap2<T, 2, true>(*this, p) : launch_remap2<T, 2, false>(*this, p);
+    else
+      rc = mapn ? launch_remap2<T, 3, true>(*this, p) : launch_remap2<T, 3, false>(*this, p);
   }
+  if (rc) return rc;
+  if (j_count == n) cur ^= 1;
   nq_cur = nq;
   return 0;
 }
@@ -736,12 +765,12 @@ extern "C" int fv3t_device_count(void) {
     CK(cudaMemcpy2DAsync(I->pe + (size_t)j * (I->n + 2) * (km + 1) + 1, (I->n + 2) * sizeof(REAL), pe1, I->n * sizeof(REAL),   \
                          I->n * sizeof(REAL), km + 1, cudaMemcpyHostToDevice, I->stream));                                     \
     /* q rows: (isd:ied) of row j for every (k, iq) */                                                                         \
-    CK(cudaMemcpy2DAsync(I->q[0] + (size_t)(j + 2) * nd, pl * sizeof(REAL), q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL),      \
+    CK(cudaMemcpy2DAsync(I->q[I->cur] + (size_t)(j + 2) * nd, pl * sizeof(REAL), q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), \
                          nd * sizeof(REAL), (size_t)km * nq, cudaMemcpyHostToDevice, I->stream));                              \
-    std::fill(I->par.begin(), I->par.end(), 0);                                                                                \
     int rc = I->remap_resident(nq, kord, fill, j - 1, 1);                                                                      \
     if (rc) return rc;                                                                                                         \
-    CK(cudaMemcpy2DAsync(q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), I->q[0] + (size_t)(j + 2) * nd, pl * sizeof(REAL),      \
+    CK(cudaMemcpy2DAsync(q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), I->q[I->cur ^ 1] + (size_t)(j + 2) * nd,                \
+                         pl * sizeof(REAL),                                                                                    \
                          nd * sizeof(REAL), (size_t)km * nq, cudaMemcpyDeviceToHost, I->stream));                              \
     CK(cudaStreamSynchronize(I->stream));                                                                                      \
     return 0;                                                                                                                  \

@@ -26,7 +26,7 @@ template <class T> struct RemapParams {
 };
 
 // cs_limiters (fv_mapz.F90:2501-2576), one element
-template <class T> __device__ __forceinline__ void cs_limiters1(bool extm, T a1, T& a2, T& a3, T& a4, int iv) {
+template <class T> FV3T_HD void cs_limiters1(bool extm, T a1, T& a2, T& a3, T& a4, int iv) {
   if (iv == 0) {
     if (a1 <= T(0)) {
       a2 = a1;
@@ -69,7 +69,7 @@ template <class T> __device__ __forceinline__ void cs_limiters1(bool extm, T a1,
 }
 
 // ppm_limiters (fv_mapz.F90:2840-2916), one element
-template <class T> __device__ __forceinline__ void ppm_limiters1(T dm, T a1, T& a2, T& a3, T& a4, int lmt) {
+template <class T> FV3T_HD void ppm_limiters1(T dm, T a1, T& a2, T& a3, T& a4, int lmt) {
   if (lmt == 3) return;
   if (lmt == 0) {
     if (dm == T(0)) {

@@ -1,0 +1,81 @@
+"""CPU check of the product's re-scheduled remap arithmetic: the __host__ __device__ column routine of
+fv3atm_b200/csrc/fv3t_remap2.cuh is compiled for the host (tests/hostsim/, test infrastructure) and must reproduce the
+oracle bit-for-bit.  The GPU build of the same template is checked by tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIM = os.path.join(HERE, "hostsim")
+NG = 3
+
+
+@pytest.fixture(scope="module")
+def sim():
+    so = os.path.join(SIM, "libhostsim.so")
+    src = os.path.join(SIM, "remap_hostsim.cu")
+    deps = [src] + [os.path.join(HERE, "..", "fv3atm_b200", "csrc", f) for f in ("fv3t_remap2.cuh", "fv3t_remap.cuh", "fv3t_common.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["nvcc", "-x", "cu", "-O2", "-std=c++17", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared", "-o", so, src],
+                       check=True, cwd=SIM)
+    return C.CDLL(so)
+
+
+def run_sim(sim, G, q, pe, ak, bk, ptop, kord, fill):
+    nt, nq, km, nd, _ = q.shape
+    n = nd - 6
+    sfx, ct = ("f64", C.c_double) if q.dtype == np.float64 else ("f32", C.c_float)
+    qs = np.ascontiguousarray(q)
+    qd = np.array(q, copy=True)
+    delp = np.zeros((nt, km, nd, nd), dtype=q.dtype)
+    kord = np.ascontiguousarray(np.broadcast_to(np.asarray(kord, dtype=np.int32), (nq,)))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    pe = np.ascontiguousarray(pe, dtype=q.dtype)
+    ak = np.ascontiguousarray(ak, dtype=q.dtype)
+    bk = np.ascontiguousarray(bk, dtype=q.dtype)
+    getattr(sim, f"hostsim_remap_{sfx}")(G, nt, n, km, nq, p(pe), p(ak), p(bk), ct(ptop), p(qs), p(qd), p(delp), p(kord), int(fill))
+    return qd, delp
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("kord", [9, 8, 10, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("G", [3, 1])
+def test_streaming_remap_is_bit_identical_to_oracle(sim, oracle, case_factory, kord, dtype, G):
+    case = case_factory(12, 32, 9, dtype)
+    qref, dref = oracle.remap_tracers(case.q, case.pe, case.ak, case.bk, case.ptop, kord, fill=True)
+    q, delp = run_sim(sim, G, case.q, case.pe, case.ak, case.bk, case.ptop, kord, True)
+    sl = slice(NG, -NG)
+    assert np.array_equal(delp[..., sl, sl], dref[..., sl, sl])
+    assert np.array_equal(q[..., sl, sl], qref[..., sl, sl]), np.abs(q[..., sl, sl] - qref[..., sl, sl]).max()
+
+
+@pytest.mark.parametrize("fill", [False, True])
+@pytest.mark.parametrize("nq,G", [(7, 3), (8, 3), (6, 2), (4, 3), (5, 2)])
+def test_ragged_tracer_groups_and_map1_q2(sim, oracle, case_factory, nq, G, fill):
+    """nq not a multiple of the group size; nq <= 5 takes the map1_q2 form of the overlap integrals."""
+    case = case_factory(12, 32, 9, "float64")
+    q0 = np.ascontiguousarray(case.q[:, :nq])
+    kord = [9, 10, 11, 12, 13, 14, 15, 16, 8][:nq]
+    qref, dref = oracle.remap_tracers(q0, case.pe, case.ak, case.bk, case.ptop, kord, fill=fill)
+    q, delp = run_sim(sim, G, q0, case.pe, case.ak, case.bk, case.ptop, kord, fill)
+    sl = slice(NG, -NG)
+    assert np.array_equal(q[..., sl, sl], qref[..., sl, sl])
+
+
+def test_fillz_paths_are_exercised(sim, oracle, case_factory):
+    """A signed tracer forces negative mapped values: top/interior/bottom borrowing and the non-local rescale."""
+    case = case_factory(12, 32, 9, "float64")
+    q0 = np.array(case.q, copy=True)
+    rng = np.random.default_rng(5)
+    q0[:, 0] = rng.standard_normal(q0[:, 0].shape) * 1e-3 + 2e-4       # many negatives
+    q0[:, 1, 0] = -np.abs(q0[:, 1, 0]) - 1e-6                          # negative top layer
+    q0[:, 2, -1] = -np.abs(q0[:, 2, -1]) - 1e-6                        # negative bottom layer
+    qref, _ = oracle.remap_tracers(q0, case.pe, case.ak, case.bk, case.ptop, 9, fill=True)
+    q, _ = run_sim(sim, 3, q0, case.pe, case.ak, case.bk, case.ptop, 9, True)
+    sl = slice(NG, -NG)
+    assert (qref[:, 0, :, sl, sl] != q0[:, 0, :, sl, sl]).any()
+    assert np.array_equal(q[..., sl, sl], qref[..., sl, sl])
