@@ -16,6 +16,7 @@
 
 #include "../../include/fv3tracer.h"
 #include "fv3t_advect.cuh"
+#include "fv3t_advect2.cuh"
 #include "fv3t_remap.cuh"
 #include "fv3t_remap2.cuh"
 
@@ -125,6 +126,7 @@ template <class T> struct Impl {
     *delp = nullptr;
   T *area = nullptr, *rarea = nullptr, *dx = nullptr, *dy = nullptr, *dxa = nullptr, *dya = nullptr, *sin_sg = nullptr;
   T *ak = nullptr, *bk = nullptr, *cmax_t = nullptr;
+  T *xfs = nullptr, *yfs = nullptr;  // xfx, yfx of tracer_2d step A (scratch, extents of cx / cy)
   T ptop = T(0);
   int *ksplt_d = nullptr, *par_d = nullptr, *cpy_d = nullptr, *kord_d = nullptr, *halo_dst = nullptr, *halo_src = nullptr;
   int cur = 0;  // outside tracer_2d every level of q lives in q[cur]; sub-step `it` reads q[(cur+it-1)&1] and writes the other
@@ -249,6 +251,8 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   CK(dalloc(&cx, sz_cx() * nt));
   CK(dalloc(&cy, sz_cx() * nt));
   CK(dalloc(&pe, sz_pe() * nt));
+  CK(dalloc(&xfs, sz_cx() * nt));
+  CK(dalloc(&yfs, sz_cx() * nt));
   CK(cudaMemsetAsync(q[0], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(q[1], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(delp, 0, sz_c() * nt * sizeof(T), stream));
@@ -323,7 +327,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -402,6 +406,15 @@ template <class T> int Impl<T>::set_cmax(const T* cmax_global, int q_split, int*
     for (int k = 0; k < npz; ++k) ksplt[k] = (q_split == 0) ? (int)(T(1) + cmax_global[k]) : nsplt;
   CK(cudaMemcpyAsync(ksplt_d, ksplt.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaStreamSynchronize(stream));
+  // steps A and C: xfx, yfx and the in-place 1/ksplt scaling of cx, cy, mfx, mfy (fv_tracer2d.F90:387-405, 449-486)
+  {
+    dim3 grid(16, nt * npz);
+    kbegin();
+    fv3t::k_prep<T><<<grid, 256, 0, stream>>>(cx, cy, mfx, mfy, xfs, yfs, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg},
+                                              ksplt_d, n, npz, nt, nsplt != 1 ? 1 : 0);
+    kend(KC_SCALE);
+    CK(cudaGetLastError());
+  }
   if (nsplt_out) *nsplt_out = nsplt;
   return 0;
 }
@@ -445,19 +458,32 @@ template <class T> int Impl<T>::halo_pack(int it, int lt, int edge, T* buf, bool
   return 0;
 }
 
-template <class T, int OI, int OO> int launch_advect(Impl<T>& c, const fv3t::AdvParams<T>& p) {
-  constexpr int TX = 32, TY = 16;
-  using TL = fv3t::AdvTile<TX, TY>;
-  auto kern = fv3t::k_advect<T, OI, OO, TX, TY>;
-  const size_t smem = TL::template smem_bytes<T>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+// strip width: threads = W + 6 (3 halo columns on either side); pick the block size that wastes the fewest lanes
+inline int pick_block(int n) {
+  const int forced = getenv("FV3T_ADV_NT") ? atoi(getenv("FV3T_ADV_NT")) : 0;  // test / tuning knob
+  if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+  int best = 32;
+  double best_eff = -1.0;
+  for (int nt = 32; nt <= 256; nt += 32) {
+    const int w = nt - 6;
+    const int strips = (n + w - 1) / w;
+    const double eff = (double)n / ((double)strips * nt);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = nt;
+    }
   }
-  dim3 grid((c.n + TX - 1) / TX, (c.n + TY - 1) / TY, c.nt * c.npz);
+  return best;
+}
+
+template <class T, int OI, int OO> int launch_advect(Impl<T>& c, fv3t::Adv2Params<T>& p) {
+  const int NT = pick_block(c.n);
+  p.W = NT - 6;
+  const int strips = (c.n + p.W - 1) / p.W;
+  dim3 grid(p.nq, strips, c.nt * c.npz);
+  const size_t smem = (size_t)6 * NT * sizeof(T);
   c.kbegin();
-  kern<<<grid, TL::NTHREADS, smem, c.stream>>>(p);
+  fv3t::k_advect2<T, OI, OO><<<grid, NT, smem, c.stream>>>(p);
   c.kend(KC_ADVECT);
   CK(cudaGetLastError());
   return 0;
@@ -466,7 +492,7 @@ template <class T, int OI, int OO> int launch_advect(Impl<T>& c, const fv3t::Adv
 // one pass of the `it` loop body (fv_tracer2d.F90:503-556) for the resident tiles
 template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   CK(cudaSetDevice(device));
-  fv3t::AdvParams<T> p;
+  fv3t::Adv2Params<T> p;
   p.qin = q[(cur + it - 1) & 1];
   p.qout = q[(cur + it) & 1];
   p.dp1 = dp1;
@@ -474,6 +500,8 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   p.mfy = mfy;
   p.cx = cx;
   p.cy = cy;
+  p.xfs = xfs;
+  p.yfs = yfs;
   p.g = fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg};
   p.ksplt = ksplt_d;
   p.n = n;
@@ -481,7 +509,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   p.nq = nq_cur;
   p.ntiles = nt;
   p.it = it;
-  p.nsplt = nsplt;
+  p.W = 0;
   p.lim_fac = lim_fac;
   int rc;
   switch (hord) {
@@ -501,7 +529,16 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     case 4: rc = launch_advect<T, 4, 4>(*this, p); break;
     default: return fail("fv3tracer: hord_tr = %d is not a scheme of xppm/yppm", hord);
   }
-  return rc;
+  if (rc) return rc;
+  // dp1 <- dp2 between sub-steps (fv_tracer2d.F90:547-553; tests the GLOBAL nsplt)
+  if (it != nsplt) {
+    dim3 grid(8, nt * npz);
+    kbegin();
+    fv3t::k_dp1_update<T><<<grid, 256, 0, stream>>>(dp1, mfx, mfy, rarea, ksplt_d, n, npz, it);
+    kend(KC_SCALE);
+    CK(cudaGetLastError());
+  }
+  return 0;
 }
 
 template <class T> int Impl<T>::finish() {
@@ -527,21 +564,6 @@ template <class T> int Impl<T>::finish() {
     }
   }
   cur = fin;
-  if (nsplt != 1) {
-    struct A {
-      T* p;
-      long plane;
-      size_t total;
-    } arr[4] = {{cx, (long)(n + 1) * (n + 6), sz_cx() * nt},
-                {cy, (long)(n + 1) * (n + 6), sz_cx() * nt},
-                {mfx, (long)(n + 1) * n, sz_mf() * nt},
-                {mfy, (long)(n + 1) * n, sz_mf() * nt}};
-    for (auto& a : arr) {
-      kbegin();
-      fv3t::k_scale_frac<T><<<1184, 256, 0, stream>>>(a.p, ksplt_d, a.plane, npz, (long)a.total);
-      kend(KC_SCALE);
-    }
-  }
   CK(cudaGetLastError());
   return 0;
 }

@@ -16,7 +16,7 @@
 namespace fv3t {
 
 // pert_ppm (tp_core.F90:1178-1236), one element
-template <class T> __device__ __forceinline__ void pert_ppm1(T a0, T& al, T& ar, int iv) {
+template <class T> FV3T_HD void pert_ppm1(T a0, T& al, T& ar, int iv) {
   if (iv == 0) {
     if (a0 <= T(0)) {
       al = T(0);
@@ -57,13 +57,13 @@ template <class T> __device__ __forceinline__ void pert_ppm1(T a0, T& al, T& ar,
 
 // two-sided edge value at a tile edge (tp_core.F90:384-385, 640-641); e0 = index of the first cell
 // inside the tile edge's far side, i.e. the formula couples cells (e0-2, e0-1 | e0, e0+1)
-template <class T, class QF, class DF> __device__ __forceinline__ T edge_value(int e0, QF q, DF dxa) {
+template <class T, class QF, class DF> FV3T_HD T edge_value(int e0, QF q, DF dxa) {
   return T(0.5) * (((T(2) * dxa(e0 - 1) + dxa(e0 - 2)) * q(e0 - 1) - dxa(e0 - 1) * q(e0 - 2)) / (dxa(e0 - 2) + dxa(e0 - 1)) +
                    ((T(2) * dxa(e0) + dxa(e0 + 1)) * q(e0) - dxa(e0) * q(e0 + 1)) / (dxa(e0) + dxa(e0 + 1)));
 }
 
 // phase "pre": dm(i) for ORD >= 7 (tp_core.F90:563-567), al(i) for ORD < 7 (:377-400)
-template <class T, int ORD, class QF, class DF> __device__ __forceinline__ T ppm_pre(int i, int npx, QF q, DF dxa) {
+template <class T, int ORD, class QF, class DF> FV3T_HD T ppm_pre(int i, int npx, QF q, DF dxa) {
   if (ORD >= 7) {
     const T qm = q(i - 1), q0 = q(i), qp = q(i + 1);
     const T xt = T(0.25) * (qp - qm);
@@ -92,7 +92,7 @@ template <class T, int ORD, class QF, class DF> __device__ __forceinline__ T ppm
 
 // phase "blbr" for cell i.  `a` = dm (ORD >= 7) or al (ORD < 7).  flg: bit0 smt5, bit1 smt6 (ORD < 7 only).
 template <class T, int ORD, class QF, class AF, class DF>
-__device__ __forceinline__ void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T lim_fac, T& bl, T& br, int& flg) {
+FV3T_HD void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T lim_fac, T& bl, T& br, int& flg) {
   flg = 0;
   const T q0 = q(i);
   if (ORD < 7) {
@@ -223,7 +223,7 @@ __device__ __forceinline__ void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T l
 
 // phase "flux" at face i (between cells i-1 and i), Courant number c (tp_core.F90:402-554, 678-701)
 template <class T, int ORD, class QF, class BLF, class BRF, class GF, class AF>
-__device__ __forceinline__ T ppm_flux(int i, T c, QF q, BLF bl, BRF br, GF flg, AF al) {
+FV3T_HD T ppm_flux(int i, T c, QF q, BLF bl, BRF br, GF flg, AF al) {
   constexpr int mord = ORD < 0 ? -ORD : ORD;
   if (ORD >= 8) {
     if (c > T(0)) {

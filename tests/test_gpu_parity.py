@@ -74,6 +74,21 @@ def test_tracer_2d_parity_config1(oracle, case_factory, n, npz):
     assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), norm_diff(got["q"], ref["q"])
 
 
+@pytest.mark.parametrize("hord", [8, 10, -5, 7])
+@pytest.mark.parametrize("nthreads", [32, 64, 96])
+def test_tracer_2d_strip_decomposition(oracle, case_factory, monkeypatch, nthreads, hord):
+    """The marching kernel splits a tile into strips of (threads - 6) columns: 1, 2 and 3 strips with ragged last
+    strips must all reproduce the oracle bit-for-bit (C40: 32 -> 26+14, 64 -> 40, 96 -> 40)."""
+    monkeypatch.setenv("FV3T_ADV_NT", str(nthreads))
+    case = case_factory(40, 8, 9, "float64", courant=1.8)
+    ref = oracle.tracer_2d(case, hord=hord)
+    got = run_gpu_tracer_2d(case, hord)
+    sl = slice(NG, -NG)
+    assert got["nsplt"] == ref["nsplt"] >= 2
+    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), norm_diff(got["q"], ref["q"])
+    assert np.array_equal(got["dp1"][..., sl, sl], ref["dp1"][..., sl, sl])
+
+
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("kord", [9, 8, 10, 11, 12, 13, 14, 15, 16, 17])
 def test_remap_parity(oracle, case_factory, kord, dtype):
