@@ -18,14 +18,21 @@ NG = cs.NG
 
 
 def fill_context(ctx, grid: cs.Grid, nq: int, courant: float = 0.7, divergent: float = 0.15, seed: int = 20260101,
-                 lagrangian_perturb: float = 0.3, device: int = 0):
-    """Fill q, dp1, cx, cy, mfx, mfy, pe of `ctx` (all six tiles resident) and set ak/bk/ptop.  Returns (ak, bk, ptop)."""
+                 lagrangian_perturb: float = 0.3, device: int = 0, q_first: int = 0):
+    """Fill q, dp1, cx, cy, mfx, mfy, pe of `ctx` (its resident tiles; tracers q_first .. q_first+nq-1 of the global
+    tracer list) and set ak/bk/ptop.  Returns (ak, bk, ptop)."""
     n, npz = ctx.n, ctx.npz
     dev = torch.device(f"cuda:{device}")
     f64 = torch.float64
     tdt = torch.float64 if ctx.dtype == np.float64 else torch.float32
 
+    tl = [t - 1 for t in ctx.tiles]
+    nt = len(tl)
+
     def T(a):
+        a = np.asarray(a)
+        if a.ndim >= 3 and a.shape[0] == 6:
+            a = a[tl]
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
     G = torch.nan_to_num(T(grid.corner_xyz))            # [6, n+7, n+7, 3]
@@ -63,7 +70,7 @@ def fill_context(ctx, grid: cs.Grid, nq: int, courant: float = 0.7, divergent: f
         arc = torch.atan2(ln, (A * B).sum(-1))
         return torch.nan_to_num((V * nrm).sum(-1) / ln * arc * ampd)
 
-    pe_run = torch.full((6, n, n), float(ptop), dtype=f64, device=dev)
+    pe_run = torch.full((nt, n, n), float(ptop), dtype=f64, device=dev)
     v_pe[:, 1:-1, 0, 1:-1] = pe_run.to(tdt)
     Cc = C[:, c0:c1, c0:c1]
     phase = 3.0 * Cc[..., 0] + 2.0 * Cc[..., 1] - 4.0 * Cc[..., 2]
@@ -137,9 +144,9 @@ def fill_context(ctx, grid: cs.Grid, nq: int, courant: float = 0.7, divergent: f
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     for iq in range(nq):
-        H, V, a, b = protos[iq % len(protos)]
-        scale = 1.0 + 0.05 * (iq // len(protos))
-        for t in range(6):
+        H, V, a, b = protos[(iq + q_first) % len(protos)]
+        scale = 1.0 + 0.05 * ((iq + q_first) // len(protos))
+        for t in range(nt):
             if H is None:
                 v_q[t, iq] = 1.0
             elif isinstance(H, str):
