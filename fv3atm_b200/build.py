@@ -11,14 +11,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfv3tracer.so")
-SOURCES = ["fv3t_api.cu"]
-HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_remap.cuh"]
+# Two translation units: the strict kernels + host orchestration keep the bit-exact contract with the FMA-free oracle
+# (no contraction, IEEE division/sqrt); the production kernels (fv3t_fast.cu) are built with FMA contraction on.
+SOURCES = {"fv3t_api.cu": ["--fmad=false"], "fv3t_fast.cu": ["--fmad=true"]}
+HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_remap.cuh",
+           "fv3t_remap2.cuh", "fv3t_fast.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    # bit-exact contract with the FMA-free oracle: no contraction, IEEE division/sqrt (nvcc defaults)
-    "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
-    "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "--prec-div=true", "--prec-sqrt=true", "--ftz=false", "--extended-lambda", "-Xcompiler", "-fPIC",
 ]
 
 
@@ -33,21 +34,33 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "fv3tracer.h")]
+    deps = [os.path.join(CSRC, f) for f in list(SOURCES) + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "fv3tracer.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
-    # the image exports CC/CXX wrappers that lack an OpenMP spec file; nvcc only needs a plain host g++
-    r = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    procs = []
+    for src, extra in SOURCES.items():
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((obj, subprocess.Popen(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for obj, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode != 0:
+            sys.stderr.write(out)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed compiling {obj}")
+        objs.append(obj)
+    # cudart is linked statically and libcuda is not linked, so the library loads on a CPU-only box
+    r = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + objs,
+                       cwd=CSRC, env=env, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libfv3tracer.so")
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libfv3tracer.so")
     return LIB
 
 

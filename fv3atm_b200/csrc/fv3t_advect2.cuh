@@ -112,9 +112,15 @@ __global__ void k_dp1_update(T* __restrict__ dp1, const T* __restrict__ mfx, con
 }
 
 // monotone slope dm of cell i from q(i-1), q(i), q(i+1)  (tp_core.F90:563-567)
+// Evaluated as min(|xt|, max(min(hi - q0, q0 - lo), 0)) with (lo, hi) = minmax(qm, qp): bit-identical to the reference
+// expression min(|xt|, max(qm,q0,qp) - q0, q0 - min(qm,q0,qp)) (when q0 lies outside [lo, hi] the reference yields +0
+// through q0 - q0) with three comparisons instead of six.
 template <class T> FV3T_HD T dm_of(T qm, T q0, T qp) {
   const T xt = T(0.25) * (qp - qm);
-  return f_sign(f_min(f_abs(xt), f_max(qm, q0, qp) - q0, q0 - f_min(qm, q0, qp)), xt);
+  const bool up = qm < qp;
+  const T lo = up ? qm : qp, hi = up ? qp : qm;
+  const T m = f_max(f_min(hi - q0, q0 - lo), T(0));
+  return f_sign(f_min(f_abs(xt), m), xt);
 }
 
 // two-sided edge value between cells (a, b | c, d) with metric (ma, mb | mc, md)  (tp_core.F90:384-385, 640-641)
@@ -301,7 +307,7 @@ template <class T, int ORD> struct YStream {
 
 // flux at x-face i from a row held in shared memory: q(gi), a(gi) (dm for ORD >= 7, al for ORD < 7) by global index
 template <class T, int ORD, class QF, class AF, class DF>
-__device__ __forceinline__ T xface_flux(int i, T cour, int npx, T lim_fac, QF q, AF a, DF dxa) {
+FV3T_HD T xface_flux(int i, T cour, int npx, T lim_fac, QF q, AF a, DF dxa) {
   if (ORD >= 8) {
     const bool up = cour > T(0);
     const int u = up ? i - 1 : i;

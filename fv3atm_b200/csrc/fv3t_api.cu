@@ -19,6 +19,7 @@
 #include "fv3t_advect2.cuh"
 #include "fv3t_remap.cuh"
 #include "fv3t_remap2.cuh"
+#include "fv3t_fast.h"
 
 namespace {
 
@@ -126,7 +127,13 @@ template <class T> struct Impl {
     *delp = nullptr;
   T *area = nullptr, *rarea = nullptr, *dx = nullptr, *dy = nullptr, *dxa = nullptr, *dya = nullptr, *sin_sg = nullptr;
   T *ak = nullptr, *bk = nullptr, *cmax_t = nullptr;
-  T *xfs = nullptr, *yfs = nullptr;  // xfx, yfx of tracer_2d step A (scratch, extents of cx / cy)
+  T *xfs = nullptr, *yfs = nullptr;  // strict mode: xfx, yfx of tracer_2d step A (scratch, extents of cx / cy; allocated on first use)
+  // fast mode (fv3t_advect3.cuh): tracer-independent per-level scratch in plane layout, allocated on first use
+  fv3t::Pair<T>*X2 = nullptr, *Y2 = nullptr, *cab = nullptr;
+  T *rrx = nullptr, *rry = nullptr;
+  bool fast = true;        // FV3T_STRICT=1 selects the bit-exact kernels for everything
+  bool prep_done = true;   // steps A/C of the current tracer_2d call have been run (done lazily by the first sub-step)
+  bool call_fast = false;  // the current tracer_2d call runs the fast kernels
   T ptop = T(0);
   int *ksplt_d = nullptr, *par_d = nullptr, *cpy_d = nullptr, *kord_d = nullptr, *halo_dst = nullptr, *halo_src = nullptr;
   int cur = 0;  // outside tracer_2d every level of q lives in q[cur]; sub-step `it` reads q[(cur+it-1)&1] and writes the other
@@ -207,6 +214,7 @@ template <class T> struct Impl {
   int halo_local(int it);
   int halo_pack(int it, int lt, int edge, T* buf, bool unpack);
   int substep(int it, int hord, T lim_fac);
+  int prepare(int hord);
   int finish();
   int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
   int remap_resident(int nq, const int* kord, int fill, int j_first, int j_count);
@@ -251,8 +259,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   CK(dalloc(&cx, sz_cx() * nt));
   CK(dalloc(&cy, sz_cx() * nt));
   CK(dalloc(&pe, sz_pe() * nt));
-  CK(dalloc(&xfs, sz_cx() * nt));
-  CK(dalloc(&yfs, sz_cx() * nt));
+  fast = !(getenv("FV3T_STRICT") && atoi(getenv("FV3T_STRICT")) != 0);
   CK(cudaMemsetAsync(q[0], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(q[1], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(delp, 0, sz_c() * nt * sizeof(T), stream));
@@ -327,7 +334,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], xfs, yfs, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -406,15 +413,7 @@ template <class T> int Impl<T>::set_cmax(const T* cmax_global, int q_split, int*
     for (int k = 0; k < npz; ++k) ksplt[k] = (q_split == 0) ? (int)(T(1) + cmax_global[k]) : nsplt;
   CK(cudaMemcpyAsync(ksplt_d, ksplt.data(), npz * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaStreamSynchronize(stream));
-  // steps A and C: xfx, yfx and the in-place 1/ksplt scaling of cx, cy, mfx, mfy (fv_tracer2d.F90:387-405, 449-486)
-  {
-    dim3 grid(16, nt * npz);
-    kbegin();
-    fv3t::k_prep<T><<<grid, 256, 0, stream>>>(cx, cy, mfx, mfy, xfs, yfs, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg},
-                                              ksplt_d, n, npz, nt, nsplt != 1 ? 1 : 0);
-    kend(KC_SCALE);
-    CK(cudaGetLastError());
-  }
+  prep_done = false;  // steps A and C run with the first sub-step, when hord (strict / fast kernels) is known
   if (nsplt_out) *nsplt_out = nsplt;
   return 0;
 }
@@ -468,7 +467,7 @@ inline int pick_block(int n) {
     const int w = nt - 6;
     const int strips = (n + w - 1) / w;
     const double eff = (double)n / ((double)strips * nt);
-    if (eff > best_eff + 1e-9) {
+    if (eff > best_eff - 1e-9) {  // ties go to the larger block (fewer strips, fewer redundant halo columns per SM)
       best_eff = eff;
       best = nt;
     }
@@ -489,9 +488,83 @@ template <class T, int OI, int OO> int launch_advect(Impl<T>& c, fv3t::Adv2Param
   return 0;
 }
 
+// steps A and C of tracer_2d: xfx, yfx and the in-place 1/ksplt scaling of cx, cy, mfx, mfy (fv_tracer2d.F90:387-405,
+// 449-486); the fast path additionally prepares 1/ra_x, 1/ra_y and the dp1/dp2 factors (fv3t_advect3.cuh, k_prep3)
+template <class T> int Impl<T>::prepare(int hord) {
+  call_fast = fast && fv3t::fast_hord_ok(hord);
+  auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+  if (call_fast) {
+    const size_t e = sz_c() * nt;
+    CK(dalloc((void**)&X2, e * sizeof(fv3t::Pair<T>)));
+    CK(dalloc((void**)&Y2, e * sizeof(fv3t::Pair<T>)));
+    CK(dalloc((void**)&cab, e * sizeof(fv3t::Pair<T>)));
+    CK(dalloc((void**)&rrx, e * sizeof(T)));
+    CK(dalloc((void**)&rry, e * sizeof(T)));
+    fv3t::Prep3Params<T> pp{cx, cy, mfx, mfy, dp1, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X2, Y2, cab, rrx, rry,
+                            ksplt_d, n, npz, nt};
+    kbegin();
+    CK(fv3t::fast_prep3<T>(pp, stream));
+    kend(KC_SCALE);
+    if (nsplt != 1) {
+      kbegin();
+      CK(fv3t::fast_scale3<T>(cx, cy, mfx, mfy, ksplt_d, n, npz, nt, stream));
+      kend(KC_SCALE);
+    }
+  } else {
+    CK(dalloc((void**)&xfs, sz_cx() * nt * sizeof(T)));
+    CK(dalloc((void**)&yfs, sz_cx() * nt * sizeof(T)));
+    dim3 grid(16, nt * npz);
+    kbegin();
+    fv3t::k_prep<T><<<grid, 256, 0, stream>>>(cx, cy, mfx, mfy, xfs, yfs, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg},
+                                              ksplt_d, n, npz, nt, nsplt != 1 ? 1 : 0);
+    kend(KC_SCALE);
+    CK(cudaGetLastError());
+  }
+  prep_done = true;
+  return 0;
+}
+
 // one pass of the `it` loop body (fv_tracer2d.F90:503-556) for the resident tiles
 template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   CK(cudaSetDevice(device));
+  if (!prep_done) {
+    const int rc = prepare(hord);
+    if (rc) return rc;
+  }
+  if (call_fast) {
+    if (!fv3t::fast_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
+    if (it > 1) {  // dp1 <- dp2 of sub-step it-1 (fv_tracer2d.F90:547-553), then dp1/dp2, 0.5*rarea/dp2 of this sub-step
+      fv3t::Cab3Params<T> cp{dp1, mfx, mfy, rarea, cab, ksplt_d, n, npz, it};
+      kbegin();
+      CK(fv3t::fast_cab3<T>(cp, nt, stream));
+      kend(KC_SCALE);
+    }
+    fv3t::Adv3Params<T> p;
+    p.qin = q[(cur + it - 1) & 1];
+    p.qout = q[(cur + it) & 1];
+    p.X2 = X2;
+    p.Y2 = Y2;
+    p.rrx = rrx;
+    p.rry = rry;
+    p.cab = cab;
+    p.mfx = mfx;
+    p.mfy = mfy;
+    p.area = area;
+    p.dxa = dxa;
+    p.dya = dya;
+    p.ksplt = ksplt_d;
+    p.n = n;
+    p.npz = npz;
+    p.nq = nq_cur;
+    p.ntiles = nt;
+    p.it = it;
+    p.W = 0;
+    p.lim_fac = lim_fac;
+    kbegin();
+    CK(fv3t::fast_advect3<T>(p, hord, pick_block(n), stream));
+    kend(KC_ADVECT);
+    return 0;
+  }
   fv3t::Adv2Params<T> p;
   p.qin = q[(cur + it - 1) & 1];
   p.qout = q[(cur + it) & 1];
@@ -587,11 +660,18 @@ template <class T> int Impl<T>::tracer_2d_resident(int nq, int hord, int q_split
 template <class T, int G, bool MAPN> int launch_remap2(Impl<T>& c, const fv3t::Remap2Params<T>& p) {
   const int cols = c.n * p.j_count;
   dim3 grid((cols + 127) / 128, c.nt, (p.nq + G - 1) / G);
+  // tuning knob: dynamic shared memory requested only to cap the resident CTAs per SM (the per-thread column scratch lives
+  // in local memory, and the resident footprint must stay inside the 126 MB L2)
+  static const int cap_smem = getenv("FV3T_REMAP_SMEM") ? atoi(getenv("FV3T_REMAP_SMEM")) : 0;
+  if (cap_smem > 48 * 1024) {
+    cudaFuncSetAttribute(fv3t::k_remap2<T, G, MAPN, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_smem);
+    cudaFuncSetAttribute(fv3t::k_remap2<T, G, MAPN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_smem);
+  }
   c.kbegin();
   if (c.npz <= 64)
-    fv3t::k_remap2<T, G, MAPN, 64><<<grid, 128, 0, c.stream>>>(p);
+    fv3t::k_remap2<T, G, MAPN, 64><<<grid, 128, cap_smem, c.stream>>>(p);
   else
-    fv3t::k_remap2<T, G, MAPN, 128><<<grid, 128, 0, c.stream>>>(p);
+    fv3t::k_remap2<T, G, MAPN, 128><<<grid, 128, cap_smem, c.stream>>>(p);
   c.kend(KC_REMAP);
   CK(cudaGetLastError());
   return 0;

@@ -1,0 +1,60 @@
+// fv3atm_b200: translation unit of the production ("fast") kernels -- compiled WITHOUT -fmad=false (see fv3t_fast.h).
+#include "fv3t_fast.h"
+
+#include <cstdlib>
+
+namespace fv3t {
+
+template <class T> cudaError_t fast_prep3(const Prep3Params<T>& p, cudaStream_t stream) {
+  dim3 grid(32, p.ntiles * p.npz);
+  k_prep3<T><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t fast_scale3(T* cx, T* cy, T* mfx, T* mfy, const int* ksplt, int n, int npz, int ntiles, cudaStream_t stream) {
+  dim3 grid(16, ntiles * npz);
+  k_scale3<T><<<grid, 256, 0, stream>>>(cx, cy, mfx, mfy, ksplt, n, npz);
+  return cudaGetLastError();
+}
+
+template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cudaStream_t stream) {
+  dim3 grid(16, ntiles * p.npz);
+  k_cab3<T><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <class T, int OI, int OO> static cudaError_t launch3(Adv3Params<T>& p, int NT, cudaStream_t stream) {
+  p.W = NT - 6;
+  const int strips = (p.n + p.W - 1) / p.W;
+  dim3 grid(p.nq, strips, p.ntiles * p.npz);
+  static const int minb = getenv("FV3T_ADV_MINB") ? atoi(getenv("FV3T_ADV_MINB")) : 2;  // tuning knob: register cap 128 (2) / 255 (1)
+  if (minb == 1)
+    k_advect3<T, OI, OO, 1><<<grid, NT, 0, stream>>>(p);
+  else
+    k_advect3<T, OI, OO, 2><<<grid, NT, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <class T> cudaError_t fast_advect3(Adv3Params<T> p, int hord, int NT, cudaStream_t stream) {
+  switch (hord) {
+    case 8: return launch3<T, 8, 8>(p, NT, stream);
+    case 10: return launch3<T, 8, 10>(p, NT, stream);  // ord_in = 8 when hord == 10 (tp_core.F90:157-161)
+    case 9: return launch3<T, 9, 9>(p, NT, stream);
+    case 11: return launch3<T, 11, 11>(p, NT, stream);
+    case 12: return launch3<T, 12, 12>(p, NT, stream);
+    case 13: return launch3<T, 13, 13>(p, NT, stream);
+    case 2: return launch3<T, 2, 2>(p, NT, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+#define FV3T_FAST_INST(T)                                                                                             \
+  template cudaError_t fast_prep3<T>(const Prep3Params<T>&, cudaStream_t);                                            \
+  template cudaError_t fast_scale3<T>(T*, T*, T*, T*, const int*, int, int, int, cudaStream_t);                       \
+  template cudaError_t fast_cab3<T>(const Cab3Params<T>&, int, cudaStream_t);                                         \
+  template cudaError_t fast_advect3<T>(Adv3Params<T>, int, int, cudaStream_t);
+FV3T_FAST_INST(double)
+FV3T_FAST_INST(float)
+
+}  // namespace fv3t

@@ -1,0 +1,20 @@
+// fv3atm_b200: launchers of the production ("fast") kernels.  They live in their own translation unit (fv3t_fast.cu,
+// built with FMA contraction on) so that the strict kernels of fv3t_api.cu keep -fmad=false and stay bit-identical
+// to the FMA-free oracle.  Each launcher enqueues on `stream` and returns cudaGetLastError().
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fv3t_advect3.cuh"
+
+namespace fv3t {
+
+// hord values whose limiter is a continuous function of its inputs: only these may use the fast path
+inline bool fast_hord_ok(int hord) { return hord == 8 || hord == 9 || hord == 11 || hord == 12 || hord == 13 || hord == 2; }
+
+template <class T> cudaError_t fast_prep3(const Prep3Params<T>& p, cudaStream_t stream);
+template <class T> cudaError_t fast_scale3(T* cx, T* cy, T* mfx, T* mfy, const int* ksplt, int n, int npz, int ntiles, cudaStream_t stream);
+template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cudaStream_t stream);
+// NT = threads per CTA (strip width NT-6); p.W is set by the launcher
+template <class T> cudaError_t fast_advect3(Adv3Params<T> p, int hord, int NT, cudaStream_t stream);
+
+}  // namespace fv3t

@@ -65,9 +65,13 @@ template <class T, class QF, class DF> FV3T_HD T edge_value(int e0, QF q, DF dxa
 // phase "pre": dm(i) for ORD >= 7 (tp_core.F90:563-567), al(i) for ORD < 7 (:377-400)
 template <class T, int ORD, class QF, class DF> FV3T_HD T ppm_pre(int i, int npx, QF q, DF dxa) {
   if (ORD >= 7) {
+    // = sign(min(|xt|, max(qm,q0,qp) - q0, q0 - min(qm,q0,qp)), xt), bit-identical, three comparisons (see dm_of)
     const T qm = q(i - 1), q0 = q(i), qp = q(i + 1);
     const T xt = T(0.25) * (qp - qm);
-    return f_sign(f_min(f_abs(xt), f_max(qm, q0, qp) - q0, q0 - f_min(qm, q0, qp)), xt);
+    const bool up = qm < qp;
+    const T lo = up ? qm : qp, hi = up ? qp : qm;
+    const T m = f_max(f_min(hi - q0, q0 - lo), T(0));
+    return f_sign(f_min(f_abs(xt), m), xt);
   } else {
     T al;
     if (i == 0) {

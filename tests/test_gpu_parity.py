@@ -1,8 +1,11 @@
 """GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
 
 Bar (BASELINE.json north_star): max normalised difference <= 1e-12 per step in fp64, <= 1e-5 in the 32-bit
-build.  The library is built FMA-free with IEEE division, the oracle likewise, so these tests additionally
-assert the stronger property that the results are bit-identical wherever that is expected."""
+build.  Two kernel sets are checked (DESIGN.md "Strict and fast kernels"):
+  strict (FV3T_STRICT=1): FMA-free, IEEE division, the reference's operation order -> additionally BIT-IDENTICAL
+                          to the (FMA-free) oracle;
+  fast   (the default):   FMA contraction, shared reciprocals -> within the bar (observed ~1e-15 in fp64).  Schemes
+                          whose limiter is discontinuous on exact zeros (hord 1, 3-7, -5) always run the strict kernels."""
 import numpy as np
 import pytest
 
@@ -32,25 +35,38 @@ def run_gpu_tracer_2d(case, hord, q_split=0, lim_fac=1.0):
 
 
 TOL = {np.dtype("float64"): 1e-12, np.dtype("float32"): 1e-5}
+FAST_HORD = {8, 9, 11, 12, 13, 2}   # fv3t::fast_hord_ok
+
+
+@pytest.fixture(params=["strict", "fast"])
+def mode(request, monkeypatch):
+    """Kernel set used by the contexts a test creates (read by fv3t_*_create)."""
+    monkeypatch.setenv("FV3T_STRICT", "1" if request.param == "strict" else "0")
+    return request.param
+
+
+def check_q(got, ref, mode, dtype, bit_exact_expected=True, what=""):
+    nd = norm_diff(got, ref)
+    assert nd.max() <= TOL[np.dtype(dtype)], f"{what}: normalised diff {nd}"
+    if mode == "strict" or bit_exact_expected:
+        sl = slice(NG, -NG)
+        assert np.array_equal(got[..., sl, sl], ref[..., sl, sl]), f"{what}: not bit-identical, nd={nd}"
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("hord", [8, 10, 9, 13, 12, 7, 11, -5, 5, 6, 1, 2, 3, 4])
-def test_tracer_2d_parity_c24(oracle, case_factory, hord, dtype):
+def test_tracer_2d_parity_c24(oracle, case_factory, hord, dtype, mode):
     case = case_factory(24, 16, 9, dtype)
     ref = oracle.tracer_2d(case, hord=hord)
     got = run_gpu_tracer_2d(case, hord)
     assert got["nsplt"] == ref["nsplt"]
     assert np.array_equal(got["ksplt"], ref["ksplt"])
-    nd = norm_diff(got["q"], ref["q"])
-    assert nd.max() <= TOL[case.dtype], f"hord={hord}: normalised diff {nd}"
-    sl = slice(NG, -NG)
-    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), f"hord={hord}: not bit-identical, nd={nd}"
+    check_q(got["q"], ref["q"], mode, dtype, bit_exact_expected=hord not in FAST_HORD, what=f"hord={hord}")
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("courant", [1.8, 3.3])
-def test_tracer_2d_subcycling(oracle, case_factory, courant, dtype):
+def test_tracer_2d_subcycling(oracle, case_factory, courant, dtype, mode):
     """nsplt > 1 with level-dependent ksplt(k): q, the advanced dp1 and the scaled cx/cy/mfx/mfy post-state."""
     case = case_factory(24, 16, 9, dtype, courant=courant)
     ref = oracle.tracer_2d(case, hord=8)
@@ -58,34 +74,34 @@ def test_tracer_2d_subcycling(oracle, case_factory, courant, dtype):
     assert ref["nsplt"] >= 2 and len(set(ref["ksplt"].tolist())) > 1
     assert got["nsplt"] == ref["nsplt"] and np.array_equal(got["ksplt"], ref["ksplt"])
     sl = slice(NG, -NG)
-    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), norm_diff(got["q"], ref["q"])
+    check_q(got["q"], ref["q"], mode, dtype, bit_exact_expected=False, what=f"courant={courant}")
+    # the caller-visible post-state of dp1, cx, cy, mfx, mfy is bit-identical in both modes
     assert np.array_equal(got["dp1"][..., sl, sl], ref["dp1"][..., sl, sl])
     for k in ("cx", "cy", "mfx", "mfy"):
         assert np.array_equal(got[k], ref[k]), k
 
 
 @pytest.mark.parametrize("n,npz", [(48, 64), (40, 8)])
-def test_tracer_2d_parity_config1(oracle, case_factory, n, npz):
-    """BASELINE config 1 (C48 L64, 9 tracers, fp64, hord 8) and a ragged size (partial 32x16 blocks)."""
+def test_tracer_2d_parity_config1(oracle, case_factory, n, npz, mode):
+    """BASELINE config 1 (C48 L64, 9 tracers, fp64, hord 8) and a ragged size (partial strips)."""
     case = case_factory(n, npz, 9, "float64")
     ref = oracle.tracer_2d(case, hord=8)
     got = run_gpu_tracer_2d(case, 8)
-    sl = slice(NG, -NG)
-    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), norm_diff(got["q"], ref["q"])
+    check_q(got["q"], ref["q"], mode, "float64", bit_exact_expected=False, what=f"C{n} L{npz}")
 
 
 @pytest.mark.parametrize("hord", [8, 10, -5, 7])
 @pytest.mark.parametrize("nthreads", [32, 64, 96])
-def test_tracer_2d_strip_decomposition(oracle, case_factory, monkeypatch, nthreads, hord):
-    """The marching kernel splits a tile into strips of (threads - 6) columns: 1, 2 and 3 strips with ragged last
-    strips must all reproduce the oracle bit-for-bit (C40: 32 -> 26+14, 64 -> 40, 96 -> 40)."""
+def test_tracer_2d_strip_decomposition(oracle, case_factory, monkeypatch, nthreads, hord, mode):
+    """The marching kernels split a tile into strips of (threads - 6) columns: 1, 2 and 3 strips with ragged last
+    strips must all reproduce the oracle (C40: 32 -> 26+14, 64 -> 40, 96 -> 40)."""
     monkeypatch.setenv("FV3T_ADV_NT", str(nthreads))
     case = case_factory(40, 8, 9, "float64", courant=1.8)
     ref = oracle.tracer_2d(case, hord=hord)
     got = run_gpu_tracer_2d(case, hord)
     sl = slice(NG, -NG)
     assert got["nsplt"] == ref["nsplt"] >= 2
-    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), norm_diff(got["q"], ref["q"])
+    check_q(got["q"], ref["q"], mode, "float64", bit_exact_expected=hord not in FAST_HORD, what=f"hord={hord} NT={nthreads}")
     assert np.array_equal(got["dp1"][..., sl, sl], ref["dp1"][..., sl, sl])
 
 
@@ -120,24 +136,29 @@ def test_remap_few_tracers_map1_q2(oracle, case_factory, kord):
     assert np.array_equal(q[..., sl, sl], qref[..., sl, sl]), norm_diff(q, qref)
 
 
-def test_step_resident_matches_host_path(oracle, case_factory):
-    """Device-resident advect + remap (the benchmarked path) against oracle advect + oracle remap."""
+def test_step_resident_matches_host_path(oracle, case_factory, mode):
+    """Device-resident advect + remap (the benchmarked path).  strict: bit-identical to oracle advect + oracle remap.
+    fast: the advected q is within the bar, and the remap -- whose kord limiters switch on the sign of differences that
+    are exactly zero around the slotted cylinder -- is bit-identical to the oracle remap of the SAME advected field."""
     case = case_factory(24, 16, 9, "float64", courant=1.8)
     ref = oracle.tracer_2d(case, hord=8)
     kord = np.array([9] * 9, dtype=np.int32)
-    qref, dref = oracle.remap_tracers(ref["q"], case.pe, case.ak, case.bk, case.ptop, kord, fill=True)
     ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
     for f in ("q", "dp1", "mfx", "mfy", "cx", "cy", "pe"):
         ctx.upload(f, getattr(case, f), case.nq)
     ctx.set_vertical(case.ak, case.bk, case.ptop)
     nsplt = ctx.tracer_2d_resident(case.nq, 8)
     assert nsplt == ref["nsplt"] and nsplt >= 2
+    qadv = np.empty_like(case.q)
+    ctx.download("q", qadv, case.nq)
+    check_q(qadv, ref["q"], mode, "float64", bit_exact_expected=False, what="advect")
     ctx.remap_tracers_resident(case.nq, kord, fill=True)
     q = np.empty_like(case.q)
     delp = np.empty_like(case.dp1)
     ctx.download("q", q, case.nq)
     ctx.download("delp", delp, case.nq)
     ctx.close()
+    qref, dref = oracle.remap_tracers(qadv, case.pe, case.ak, case.bk, case.ptop, kord, fill=True)
     sl = slice(NG, -NG)
     assert np.array_equal(q[..., sl, sl], qref[..., sl, sl]), norm_diff(q, qref)
     assert np.array_equal(delp[..., sl, sl], dref[..., sl, sl])
