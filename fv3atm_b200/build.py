@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libfv3tracer.so")
 # (no contraction, IEEE division/sqrt); the production kernels (fv3t_fast.cu) are built with FMA contraction on.
 SOURCES = {"fv3t_api.cu": ["--fmad=false"], "fv3t_fast.cu": ["--fmad=true"]}
 HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_remap.cuh",
-           "fv3t_remap2.cuh", "fv3t_fast.h"]
+           "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

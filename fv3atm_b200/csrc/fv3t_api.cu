@@ -131,6 +131,8 @@ template <class T> struct Impl {
   // fast mode (fv3t_advect3.cuh): tracer-independent per-level scratch in plane layout, allocated on first use
   fv3t::Pair<T>*X2 = nullptr, *Y2 = nullptr, *cab = nullptr;
   T *rrx = nullptr, *rry = nullptr;
+  fv3t::Pair<T>*P1 = nullptr, *P2 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
+  T* R2 = nullptr;
   bool fast = true;        // FV3T_STRICT=1 selects the bit-exact kernels for everything
   bool prep_done = true;   // steps A/C of the current tracer_2d call have been run (done lazily by the first sub-step)
   bool call_fast = false;  // the current tracer_2d call runs the fast kernels
@@ -334,7 +336,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, P1, P2, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -689,7 +691,26 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
   if (!mapn)
     for (int iq = 0; iq < nq; ++iq) need_ppm |= kord[iq] <= 7;
   int rc = 0;
-  if (need_ppm) {
+  bool fast_ok = fast && mapn && j_count == n && npz <= 128;
+  const int ak0 = kord[0] < 0 ? -kord[0] : kord[0];
+  for (int iq = 0; iq < nq; ++iq) {
+    const int a = kord[iq] < 0 ? -kord[iq] : kord[iq];
+    fast_ok = fast_ok && fv3t::fast_kord_ok(a) && (a == ak0 || (a <= 8 && ak0 <= 8) || (a >= 17 && ak0 >= 17));
+  }
+  if (fast_ok) {
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+    const size_t e1 = plane() * (npz + 1) * nt;
+    CK(dalloc((void**)&P1, e1 * sizeof(fv3t::Pair<T>)));
+    CK(dalloc((void**)&P2, e1 * sizeof(fv3t::Pair<T>)));
+    CK(dalloc((void**)&R2, sz_c() * nt * sizeof(T)));
+    fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, P2, R2, ptop, n, npz, nq, nt, fill};
+    kbegin();
+    CK(fv3t::fast_remap_coef3<T>(p, stream));
+    kend(KC_SCALE);
+    kbegin();
+    CK(fv3t::fast_remap3<T>(p, ak0, stream));
+    kend(KC_REMAP);
+  } else if (need_ppm) {
     fv3t::RemapParams<T> p;
     p.q0 = q[cur];
     p.q1 = q[cur];

@@ -49,11 +49,37 @@ template <class T> cudaError_t fast_advect3(Adv3Params<T> p, int hord, int NT, c
   }
 }
 
+template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaStream_t stream) {
+  dim3 grid((p.n * p.n + 127) / 128, p.ntiles);
+  k_remap_coef3<T><<<grid, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <class T, int AK> static cudaError_t launch_remap3(const Remap3Params<T>& p, cudaStream_t stream) {
+  dim3 grid((p.n * p.n + 127) / 128, p.ntiles, p.nq);
+  k_remap3<T, AK, true, 128><<<grid, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <class T> cudaError_t fast_remap3(const Remap3Params<T>& p, int akord, cudaStream_t stream) {
+  if (akord <= 8) return launch_remap3<T, 8>(p, stream);
+  if (akord >= 17) return launch_remap3<T, 17>(p, stream);
+  switch (akord) {
+    case 9: return launch_remap3<T, 9>(p, stream);
+    case 12: return launch_remap3<T, 12>(p, stream);
+    case 13: return launch_remap3<T, 13>(p, stream);
+    case 14: return launch_remap3<T, 14>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 #define FV3T_FAST_INST(T)                                                                                             \
   template cudaError_t fast_prep3<T>(const Prep3Params<T>&, cudaStream_t);                                            \
   template cudaError_t fast_scale3<T>(T*, T*, T*, T*, const int*, int, int, int, cudaStream_t);                       \
   template cudaError_t fast_cab3<T>(const Cab3Params<T>&, int, cudaStream_t);                                         \
-  template cudaError_t fast_advect3<T>(Adv3Params<T>, int, int, cudaStream_t);
+  template cudaError_t fast_advect3<T>(Adv3Params<T>, int, int, cudaStream_t);                                        \
+  template cudaError_t fast_remap_coef3<T>(const Remap3Params<T>&, cudaStream_t);                                     \
+  template cudaError_t fast_remap3<T>(const Remap3Params<T>&, int, cudaStream_t);
 FV3T_FAST_INST(double)
 FV3T_FAST_INST(float)
 

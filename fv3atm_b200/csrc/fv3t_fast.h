@@ -5,12 +5,20 @@
 #include <cuda_runtime.h>
 
 #include "fv3t_advect3.cuh"
+#include "fv3t_remap3.cuh"
 
 namespace fv3t {
 
 // hord values whose limiter is a continuous function of its inputs: only these may use the fast path
 inline bool fast_hord_ok(int hord) { return hord == 8 || hord == 9 || hord == 11 || hord == 12 || hord == 13 || hord == 2; }
 
+// abs(kord) values whose limiter decisions depend only on the INPUT cell means (not on computed interface values): only
+// these may use the fast remap (kord 10, 11, 15, 16 compare computed quantities that are exactly equal on flat data)
+inline bool fast_kord_ok(int akord) { return akord <= 9 || akord == 12 || akord == 13 || akord == 14 || akord >= 17; }
+
+template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaStream_t stream);
+// all tracers share abs(kord) = akord (8 stands for every value <= 8, 17 for every value >= 17); mapn_tracer form (nq > 5)
+template <class T> cudaError_t fast_remap3(const Remap3Params<T>& p, int akord, cudaStream_t stream);
 template <class T> cudaError_t fast_prep3(const Prep3Params<T>& p, cudaStream_t stream);
 template <class T> cudaError_t fast_scale3(T* cx, T* cy, T* mfx, T* mfy, const int* ksplt, int n, int npz, int ntiles, cudaStream_t stream);
 template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cudaStream_t stream);
