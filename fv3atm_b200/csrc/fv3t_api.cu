@@ -131,8 +131,8 @@ template <class T> struct Impl {
   // fast mode (fv3t_advect3.cuh): tracer-independent per-level scratch in plane layout, allocated on first use
   fv3t::Pair<T>*X2 = nullptr, *Y2 = nullptr, *cab = nullptr;
   T *rrx = nullptr, *rry = nullptr;
-  fv3t::Pair<T>*P1 = nullptr, *P2 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
-  T* R2 = nullptr;
+  fv3t::Pair<T>* P1 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
+  T *GAM = nullptr, *RD1 = nullptr, *R2 = nullptr;
   bool fast = true;        // FV3T_STRICT=1 selects the bit-exact kernels for everything
   bool prep_done = true;   // steps A/C of the current tracer_2d call have been run (done lazily by the first sub-step)
   bool call_fast = false;  // the current tracer_2d call runs the fast kernels
@@ -336,7 +336,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, P1, P2, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -701,9 +701,10 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
     auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
     const size_t e1 = plane() * (npz + 1) * nt;
     CK(dalloc((void**)&P1, e1 * sizeof(fv3t::Pair<T>)));
-    CK(dalloc((void**)&P2, e1 * sizeof(fv3t::Pair<T>)));
+    CK(dalloc((void**)&GAM, e1 * sizeof(T)));
+    CK(dalloc((void**)&RD1, sz_c() * nt * sizeof(T)));
     CK(dalloc((void**)&R2, sz_c() * nt * sizeof(T)));
-    fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, P2, R2, ptop, n, npz, nq, nt, fill};
+    fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, nq, nt, fill};
     kbegin();
     CK(fv3t::fast_remap_coef3<T>(p, stream));
     kend(KC_SCALE);

@@ -56,7 +56,7 @@ template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaSt
 }
 
 template <class T, int AK> static cudaError_t launch_remap3(const Remap3Params<T>& p, cudaStream_t stream) {
-  dim3 grid((p.n * p.n + 127) / 128, p.ntiles, p.nq);
+  dim3 grid(p.nq, (p.n * p.n + 127) / 128, p.ntiles);
   k_remap3<T, AK, true, 128><<<grid, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }

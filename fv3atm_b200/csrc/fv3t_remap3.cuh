@@ -27,7 +27,8 @@ template <class T> struct Remap3Params {
   const T *ak, *bk;
   T* delp;         // (isd:ied, jsd:jed, km) tile-major
   Pair<T>* P1;     // (isd:ied, jsd:jed, km+1): {d4, 1/bet}; level 1 {ctop, 1/bet1}; level km+1 {cbot, a_bot}
-  Pair<T>* P2;     // (isd:ied, jsd:jed, km+1): {gam, 1/dp1};                        level km+1 {1/den, 0}
+  T* GAM;          // (isd:ied, jsd:jed, km+1): gam;   level km+1: 1/den
+  T* RD1;          // (isd:ied, jsd:jed, km):   1/dp1
   T* R2;           // (isd:ied, jsd:jed, km): 1/dp2
   T ptop;
   int n, km, nq, ntiles, fill;
@@ -41,7 +42,8 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
   const T* pe = p.pe + (long)t * pe_ld2 * (n + 2) + (long)i + (long)j * pe_ld2;
   const long col = (long)(j + 2) * nd + (i + 2);
   Pair<T>* P1 = p.P1 + (long)t * plane * (km + 1) + col;
-  Pair<T>* P2 = p.P2 + (long)t * plane * (km + 1) + col;
+  T* GAM = p.GAM + (long)t * plane * (km + 1) + col;
+  T* RD1 = p.RD1 + (long)t * plane * km + col;
   T* R2 = p.R2 + (long)t * plane * km + col;
   T* delp = p.delp + (long)t * plane * km + col;
   auto PE1 = [&](int k) -> T { return pe[(long)(k - 1) * pe_ld1]; };
@@ -53,14 +55,16 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
   T bet = grat * (grat + T(0.5));
   P1[0] = Pair<T>{(grat + grat) * (grat + T(1)), T(1) / bet};
   T gprev = (T(1) + grat * (grat + T(1.5))) / bet;
-  P2[0] = Pair<T>{gprev, T(1) / dpm};
+  GAM[0] = gprev;
+  RD1[0] = T(1) / dpm;
   T d4 = T(0);
   for (int k = 2; k <= km; ++k) {
     d4 = dpm / dpc;
     bet = T(2) + d4 + d4 - gprev;
     gprev = d4 / bet;
     P1[(long)(k - 1) * plane] = Pair<T>{d4, T(1) / bet};
-    P2[(long)(k - 1) * plane] = Pair<T>{gprev, T(1) / dpc};
+    GAM[(long)(k - 1) * plane] = gprev;
+    RD1[(long)(k - 1) * plane] = T(1) / dpc;
     if (k < km) {
       pb = pc;
       pc = PE1(k + 2);
@@ -72,7 +76,7 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
   const T cbot = T(2) * d4 * (d4 + T(1));
   const T den = d4 * (d4 + T(0.5)) - a_bot * gprev;
   P1[(long)km * plane] = Pair<T>{cbot, a_bot};
-  P2[(long)km * plane] = Pair<T>{T(1) / den, T(0)};
+  GAM[(long)km * plane] = T(1) / den;
   T p2a = PE2(1);
   for (int k = 1; k <= km; ++k) {
     const T p2b = PE2(k + 1);
@@ -95,7 +99,8 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
   const T* qs = p.qsrc + off;
   T* qd = p.qdst + off;
   const Pair<T>* P1 = p.P1 + (long)t * plane * (km + 1) + col;
-  const Pair<T>* P2 = p.P2 + (long)t * plane * (km + 1) + col;
+  const T* GAM = p.GAM + (long)t * plane * (km + 1) + col;
+  const T* RD1 = p.RD1 + (long)t * plane * km + col;
   const T* R2 = p.R2 + (long)t * plane * km + col;
   auto A1 = [&](int k) -> T { return qs[(long)(k - 1) * plane]; };
   auto PE1 = [&](int k) -> T { return pe[(long)(k - 1) * pe_ld1]; };
@@ -104,64 +109,85 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
 
   T qv[KM + 2];
 
-  // ---- pass 1: forward sweep (fv_mapz.F90:1736-1750) with the stored d4, 1/bet
+  // ---- pass 1: forward sweep (fv_mapz.F90:1736-1750) with the stored d4, 1/bet.  Loads are issued a chunk of CH levels
+  //      ahead of the dependent recurrence: the column walks through HBM with a plane-sized stride, and nothing but
+  //      memory-level parallelism hides that latency (profiles/r01_remap3_v0_ncu.txt: 8 of 12 stall cycles per issue)
+  constexpr int CH = 8;
   {
     T a1mm = A1(1), a1m = A1(2);
     const Pair<T> c1 = P1[0];
     T qk = (c1.a * a1mm + a1m) * c1.b;
     qv[1] = qk;
-#pragma unroll 4
-    for (int k = 2; k <= km; ++k) {
-      const Pair<T> ck = P1[(long)(k - 1) * plane];
-      qk = (T(3) * (a1mm + ck.a * a1m) - qk) * ck.b;
-      qv[k] = qk;
-      if (k < km) {
-        a1mm = a1m;
-        a1m = A1(k + 1);
+    for (int k0 = 2; k0 <= km; k0 += CH) {
+      T an[CH];
+      Pair<T> ck[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int k = k0 + u;
+        ck[u] = (k <= km) ? P1[(long)(k - 1) * plane] : Pair<T>{T(0), T(0)};
+        an[u] = (k + 1 <= km) ? A1(k + 1) : T(0);
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int k = k0 + u;
+        if (k <= km) {
+          qk = (T(3) * (a1mm + ck[u].a * a1m) - qk) * ck[u].b;
+          qv[k] = qk;
+          if (k < km) {
+            a1mm = a1m;
+            a1m = an[u];
+          }
+        }
       }
     }
     const Pair<T> cb = P1[(long)km * plane];
-    const T rden = P2[(long)km * plane].a;
+    const T rden = GAM[(long)km * plane];
     qv[km + 1] = (cb.a * a1m + a1mm - cb.b * qk) * rden;
   }
 
   // ---- pass 2: back-substitution (fv_mapz.F90:1757-1762) + interface constraints (:1783-1818); iv = 0
   {
     T r = qv[km + 1];
-    if (AK > 16) {
-#pragma unroll 4
-      for (int k = km; k >= 1; --k) {
-        r = qv[k] - P2[(long)(k - 1) * plane].a * r;
-        qv[k] = r;
+    T ap = T(0), a0 = A1(km), am = A1(km - 1), amm = A1(km - 2);
+    for (int k0 = km; k0 >= 1; k0 -= CH) {
+      T qq[CH], gg[CH], an[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int k = k0 - u;
+        qq[u] = k >= 1 ? qv[k] : T(0);
+        gg[u] = k >= 1 ? GAM[(long)(k - 1) * plane] : T(0);
+        an[u] = (AK <= 16 && k - 3 >= 1) ? A1(k - 3) : T(0);
       }
-    } else {
-      T ap = T(0), a0 = A1(km), am = A1(km - 1), amm = A1(km - 2);
-#pragma unroll 4
-      for (int k = km; k >= 1; --k) {
-        const T an = (k - 3 >= 1) ? A1(k - 3) : T(0);
-        r = qv[k] - P2[(long)(k - 1) * plane].a * r;
-        T c = r;
-        if (k == km || k == 2) {
-          c = f_min(c, f_max(am, a0));
-          c = f_max(c, f_min(am, a0));
-        } else if (k >= 3) {
-          const T gm = am - amm;  // gam(k-1) = a1(k-1) - a1(k-2)
-          const T gp = ap - a0;   // gam(k+1) = a1(k+1) - a1(k)
-          if (gm * gp > T(0)) {
-            c = f_min(c, f_max(am, a0));
-            c = f_max(c, f_min(am, a0));
-          } else if (gm > T(0)) {
-            c = f_max(c, f_min(am, a0));
-          } else {
-            c = f_min(c, f_max(am, a0));
-            c = f_max(T(0), c);
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int k = k0 - u;
+        if (k >= 1) {
+          r = qq[u] - gg[u] * r;
+          T c = r;
+          if (AK <= 16) {
+            if (k == km || k == 2) {
+              c = f_min(c, f_max(am, a0));
+              c = f_max(c, f_min(am, a0));
+            } else if (k >= 3) {
+              const T gm = am - amm;  // gam(k-1) = a1(k-1) - a1(k-2)
+              const T gp = ap - a0;   // gam(k+1) = a1(k+1) - a1(k)
+              if (gm * gp > T(0)) {
+                c = f_min(c, f_max(am, a0));
+                c = f_max(c, f_min(am, a0));
+              } else if (gm > T(0)) {
+                c = f_max(c, f_min(am, a0));
+              } else {
+                c = f_min(c, f_max(am, a0));
+                c = f_max(T(0), c);
+              }
+            }
+            ap = a0;
+            a0 = am;
+            am = amm;
+            amm = an[u];
           }
+          qv[k] = c;
         }
-        qv[k] = c;
-        ap = a0;
-        a0 = am;
-        am = amm;
-        amm = an;
       }
     }
   }
@@ -242,7 +268,7 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
   };
 
   T pe1lo = PE1(1), pe1hi = PE1(2);
-  T rdp1 = P2[0].b;
+  T rdp1 = RD1[0];
   for (int l = 1; k <= km; ++l) {
     const bool have = l <= km;
     const T dp1l = pe1hi - pe1lo;
@@ -320,7 +346,7 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
     if (l < km) {
       pe1lo = pe1hi;
       pe1hi = PE1(l + 2);
-      rdp1 = P2[(long)l * plane].b;
+      rdp1 = RD1[(long)l * plane];
       a_0 = a_p1;
       a_p1 = a_p2;
       a_p2 = (l + 3 <= km) ? A1(l + 3) : T(0);
@@ -356,9 +382,11 @@ template <class T> __global__ void __launch_bounds__(128) k_remap_coef3(const Re
 }
 template <class T, int AK, bool MAPN, int KM> __global__ void __launch_bounds__(128, 4) k_remap3(const Remap3Params<T> p) {
   const int cols = p.n * p.n;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // blockIdx.x = tracer: the nq CTAs of one column block are adjacent in the grid, run together and share P1, GAM, RD1, R2, pe
+  // through L2 (with the tracer as the slowest index every tracer streamed them from HBM again: 64 of 121 B per update)
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  remap3_column<T, AK, MAPN, KM>(p, blockIdx.y, c % p.n + 1, c / p.n + 1, blockIdx.z);
+  remap3_column<T, AK, MAPN, KM>(p, blockIdx.z, c % p.n + 1, c / p.n + 1, blockIdx.x);
 }
 #endif
 

@@ -18,9 +18,9 @@ template <class T>
 static int run(int ntiles, int n, int km, int nq, const T* pe, const T* ak, const T* bk, T ptop, const T* qsrc, T* qdst, T* delp,
                int akord, int fill) {
   const long plane = (long)(n + 6) * (n + 6);
-  std::vector<Pair<T>> P1((size_t)ntiles * plane * (km + 1)), P2((size_t)ntiles * plane * (km + 1));
-  std::vector<T> R2((size_t)ntiles * plane * km);
-  Remap3Params<T> p{qsrc, qdst, pe, ak, bk, delp, P1.data(), P2.data(), R2.data(), ptop, n, km, nq, ntiles, fill};
+  std::vector<Pair<T>> P1((size_t)ntiles * plane * (km + 1));
+  std::vector<T> GAM((size_t)ntiles * plane * (km + 1)), RD1((size_t)ntiles * plane * km), R2((size_t)ntiles * plane * km);
+  Remap3Params<T> p{qsrc, qdst, pe, ak, bk, delp, P1.data(), GAM.data(), RD1.data(), R2.data(), ptop, n, km, nq, ntiles, fill};
   for (int t = 0; t < ntiles; ++t)
     for (int j = 1; j <= n; ++j)
       for (int i = 1; i <= n; ++i) remap_coef_column<T>(p, t, i, j);

@@ -113,8 +113,11 @@ def run_sim3(sim3, q, pe, ak, bk, ptop, akord, fill):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("kord", [9, 8, 10, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("kord", [9, 8, 12, 13, 14, 17])
 def test_fast_remap_matches_oracle(sim3, oracle, case_factory, kord, dtype):
+    """The limiters the product runs on the fast path (fv3t::fast_kord_ok).  kord 10, 11, 15, 16 compare COMPUTED interface
+    values (ext5 / ext6, fv_mapz.F90:1820-1846) that are exactly equal on flat data, so any re-association flips them: the
+    product keeps those on its bit-exact strict kernel."""
     case = case_factory(12, 32, 9, dtype)
     qref, dref = oracle.remap_tracers(case.q, case.pe, case.ak, case.bk, case.ptop, kord, fill=True)
     q, delp = run_sim3(sim3, case.q, case.pe, case.ak, case.bk, case.ptop, kord, True)
