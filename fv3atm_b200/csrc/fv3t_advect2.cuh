@@ -315,8 +315,8 @@ FV3T_HD T xface_flux(int i, T cour, int npx, T lim_fac, QF q, AF a, DF dxa) {
     int flg;
     ppm_blbr<T, ORD>(u, npx, q, a, dxa, lim_fac, bl, br, flg);
     const T qu = q(u);
-    if (up) return qu + (T(1) - cour) * (br - cour * (bl + br));
-    return qu + (T(1) + cour) * (bl + cour * (bl + br));
+    const T a = f_abs(cour);  // see ppm_flux: one expression for both wind directions, bit-identical to the reference's two
+    return qu + (T(1) - a) * ((up ? br : bl) - a * (bl + br));
   } else {
     T blm, brm, bl0, br0;
     int fm, f0;

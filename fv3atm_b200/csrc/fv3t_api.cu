@@ -563,7 +563,11 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     p.W = 0;
     p.lim_fac = lim_fac;
     kbegin();
-    CK(fv3t::fast_advect3<T>(p, hord, pick_block(n), stream));
+    // 64-thread CTAs (58-column strips): measured fastest on B200 at C768 (131 ms vs 143 / 147 / 153 ms for 96 / 128 / 160
+    // threads, profiles/r01_advect3_block_sweep.txt): three barriers per row step cost least when a CTA is two warps
+    const int forced = getenv("FV3T_ADV_NT") ? atoi(getenv("FV3T_ADV_NT")) : 0;
+    const int NT = (forced >= 32 && forced <= 256 && forced % 32 == 0) ? forced : 64;
+    CK(fv3t::fast_advect3<T>(p, hord, NT, stream));
     kend(KC_ADVECT);
     return 0;
   }

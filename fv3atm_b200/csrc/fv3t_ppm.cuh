@@ -230,13 +230,13 @@ template <class T, int ORD, class QF, class BLF, class BRF, class GF, class AF>
 FV3T_HD T ppm_flux(int i, T c, QF q, BLF bl, BRF br, GF flg, AF al) {
   constexpr int mord = ORD < 0 ? -ORD : ORD;
   if (ORD >= 8) {
-    if (c > T(0)) {
-      const T blm = bl(i - 1), brm = br(i - 1);
-      return q(i - 1) + (T(1) - c) * (brm - c * (blm + brm));
-    } else {
-      const T bl0 = bl(i), br0 = br(i);
-      return q(i) + (T(1) + c) * (bl0 + c * (bl0 + br0));
-    }
+    // one evaluation for both wind directions: with a = |c| the upwind cell u gives q(u) + (1-a)*(b - a*(bl+br)), b = br for
+    // c > 0 and bl otherwise -- bit-identical to the reference's two expressions (1+c = 1-a and bl + c*s = bl - a*s exactly)
+    const bool up = c > T(0);
+    const T a = f_abs(c);
+    const T blu = up ? bl(i - 1) : bl(i), bru = up ? br(i - 1) : br(i), qu = up ? q(i - 1) : q(i);
+    const T b = up ? bru : blu;
+    return qu + (T(1) - a) * (b - a * (blu + bru));
   } else if (ORD == 7) {
     const T blm = bl(i - 1), brm = br(i - 1), bl0 = bl(i), br0 = br(i);
     const bool s = (blm * brm < T(0)) || (bl0 * br0 < T(0));

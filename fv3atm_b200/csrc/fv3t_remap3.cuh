@@ -88,7 +88,8 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
 }
 
 // ---- one column of one tracer; AK = abs(kord) -----------------------------------------------------------------------------
-template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const Remap3Params<T>& p, int t, int i, int j, int iq) {
+template <class T, int AK, bool MAPN, int KM>
+FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp, int t, int i, int j, int iq) {
   const int n = p.n, km = p.km;
   const long nd = n + 6, plane = nd * nd;
   const T r3 = K<T>::r3(), r23 = K<T>::r23();
@@ -96,8 +97,8 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
   const T* pe = p.pe + (long)t * pe_ld2 * (n + 2) + (long)i + (long)j * pe_ld2;  // pe1(k) = pe[(k-1)*pe_ld1]
   const long col = (long)(j + 2) * nd + (i + 2);
   const long off = (((long)t * p.nq + iq) * km) * plane + col;
-  const T* qs = p.qsrc + off;
-  T* qd = p.qdst + off;
+  const T* __restrict__ qs = p.qsrc + off;
+  T* __restrict__ qd = p.qdst + off;
   const Pair<T>* P1 = p.P1 + (long)t * plane * (km + 1) + col;
   const T* GAM = p.GAM + (long)t * plane * (km + 1) + col;
   const T* RD1 = p.RD1 + (long)t * plane * km + col;
@@ -105,7 +106,7 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
   auto A1 = [&](int k) -> T { return qs[(long)(k - 1) * plane]; };
   auto PE1 = [&](int k) -> T { return pe[(long)(k - 1) * pe_ld1]; };
   const T ps = PE1(km + 1);
-  auto PE2 = [&](int k) -> T { return k == 1 ? p.ptop : (k == km + 1 ? ps : add_rn(p.ak[k - 1], mul_rn(p.bk[k - 1], ps))); };  // uncontracted: delp is caller-visible
+  auto PE2 = [&](int k) -> T { return k == 1 ? p.ptop : (k == km + 1 ? ps : add_rn(akp[k - 1], mul_rn(bkp[k - 1], ps))); };  // uncontracted: delp is caller-visible
 
   T qv[KM + 2];
 
@@ -272,6 +273,14 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
   for (int l = 1; k <= km; ++l) {
     const bool have = l <= km;
     const T dp1l = pe1hi - pe1lo;
+    // inputs of the NEXT source layer, requested before this layer's arithmetic so that their latency hides behind it
+    T n_pe = T(0), n_rd = T(0), n_a = T(0), n_c = T(0);
+    if (l < km) {
+      n_pe = PE1(l + 2);
+      n_rd = RD1[(long)l * plane];
+      n_a = (l + 3 <= km) ? A1(l + 3) : T(0);
+      n_c = (l + 3 <= km + 1) ? qv[l + 3] : T(0);
+    }
     // ---- limited parabola of source layer l
     T a2 = c_0, a3 = c_p1, a4 = T(0);
     if (!have) {
@@ -345,14 +354,14 @@ template <class T, int AK, bool MAPN, int KM> FV3T_HD void remap3_column(const R
     // ---- advance the generators to source layer l+1
     if (l < km) {
       pe1lo = pe1hi;
-      pe1hi = PE1(l + 2);
-      rdp1 = RD1[(long)l * plane];
+      pe1hi = n_pe;
+      rdp1 = n_rd;
       a_0 = a_p1;
       a_p1 = a_p2;
-      a_p2 = (l + 3 <= km) ? A1(l + 3) : T(0);
+      a_p2 = n_a;
       c_0 = c_p1;
       c_p1 = c_p2;
-      c_p2 = (l + 3 <= km + 1) ? qv[l + 3] : T(0);
+      c_p2 = n_c;
       g_m1 = g_0;
       g_0 = g_p1;
       g_p1 = g_p2;
@@ -381,12 +390,19 @@ template <class T> __global__ void __launch_bounds__(128) k_remap_coef3(const Re
   remap_coef_column<T>(p, blockIdx.y, c % p.n + 1, c / p.n + 1);
 }
 template <class T, int AK, bool MAPN, int KM> __global__ void __launch_bounds__(128, 4) k_remap3(const Remap3Params<T> p) {
+  // ak, bk in shared memory: pe2(k) = ak + bk*ps sits on the dependent path of the target-layer loop
+  __shared__ T s_ak[KM + 1], s_bk[KM + 1];
+  for (int k = threadIdx.x; k <= p.km; k += blockDim.x) {
+    s_ak[k] = p.ak[k];
+    s_bk[k] = p.bk[k];
+  }
+  __syncthreads();
   const int cols = p.n * p.n;
   // blockIdx.x = tracer: the nq CTAs of one column block are adjacent in the grid, run together and share P1, GAM, RD1, R2, pe
   // through L2 (with the tracer as the slowest index every tracer streamed them from HBM again: 64 of 121 B per update)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  remap3_column<T, AK, MAPN, KM>(p, blockIdx.z, c % p.n + 1, c / p.n + 1, blockIdx.x);
+  remap3_column<T, AK, MAPN, KM>(p, s_ak, s_bk, blockIdx.z, c % p.n + 1, c / p.n + 1, blockIdx.x);
 }
 #endif
 
