@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+grep -E "FAILED|passed|failed|^E  " gpurun_out/pytest_gpu.log | cut -c1-400 | tail -25

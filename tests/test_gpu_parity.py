@@ -180,3 +180,138 @@ def test_step_resident_matches_host_path(oracle, case_factory, mode):
     sl = slice(NG, -NG)
     check_q(q, qref, mode, "float64", bit_exact_expected=False, what="remap of the advected field")
     assert np.array_equal(delp[..., sl, sl], dref[..., sl, sl])
+
+
+def test_multi_step_mass_conservation_and_positivity(case_factory, mode):
+    """BASELINE config 2 in miniature (C96, hord_tr 8 / kord_tr 9, device-resident multi-step run): flux form conserves the
+    global tracer mass sum(q*dp*area) through tracer_2d, the remap conserves the mass it is handed (measured in the
+    Lagrangian layers of pe) -- both to <= 1e-13 relative per step -- and the positive tracers stay non-negative.
+    Size-independent properties: no oracle involved."""
+    case = case_factory(96, 8, 9, "float64", courant=0.7)
+    ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+    for f in ("q", "dp1", "mfx", "mfy", "cx", "cy", "pe"):
+        ctx.upload(f, getattr(case, f), case.nq)
+    ctx.set_vertical(case.ak, case.bk, case.ptop)
+    kord = np.full(case.nq, 9, dtype=np.int32)
+    sl = slice(NG, -NG)
+    area = case.metrics()["area"][:, None, None, sl, sl]
+    rarea = case.metrics()["rarea"][:, None, sl, sl]
+    dp1 = case.dp1[:, None, :, sl, sl]
+    dp2 = (case.dp1[..., sl, sl] + (case.mfx[..., :, :-1] - case.mfx[..., :, 1:] + case.mfy[..., :-1, :] - case.mfy[..., 1:, :]) * rarea)[:, None]
+    dp_lag = np.diff(case.pe, axis=2).transpose(0, 2, 1, 3)[:, None, :, 1:-1, 1:-1]
+    positive = case.q[..., sl, sl].min(axis=(0, 2, 3, 4)) >= 0
+    assert positive.sum() >= 6
+    q = np.empty_like(case.q)
+    delp = np.empty_like(case.dp1)
+
+    def mass(thick):
+        return (q[..., sl, sl] * thick * area).sum(axis=(0, 2, 3, 4))
+
+    for step in range(4):
+        ctx.download("q", q, case.nq)
+        m0 = mass(dp1)
+        assert ctx.tracer_2d_resident(case.nq, 8) == 1
+        ctx.download("q", q, case.nq)
+        m1 = mass(dp2)
+        assert (np.abs(m1 - m0) <= 1e-13 * np.abs(m0)).all(), (step, (m1 - m0) / m0)
+        assert (q[..., sl, sl].min(axis=(0, 2, 3, 4))[positive] >= 0).all()
+        ml = mass(dp_lag)
+        ctx.remap_tracers_resident(case.nq, kord, fill=True)
+        ctx.download("q", q, case.nq)
+        ctx.download("delp", delp, case.nq)
+        m2 = mass(delp[:, None, :, sl, sl])
+        assert (np.abs(m2 - ml)[positive] <= 1e-13 * np.abs(ml)[positive]).all(), (step, ((m2 - ml) / ml)[positive])
+        assert (q[..., sl, sl].min(axis=(0, 2, 3, 4))[positive] >= 0).all()
+    ctx.close()
+
+
+# ---- edge cases and BASELINE configurations -----------------------------------------------------------------------------
+def _remap_gpu(case, q0, kord, fill=True):
+    ctx = TracerContext(case.n + 1, case.npz, q0.shape[1], case.metrics(), dtype=case.dtype)
+    q = np.array(q0, copy=True)
+    delp = np.zeros_like(case.dp1)
+    ctx.remap_tracers(case.pe, case.ak, case.bk, case.ptop, q, delp, kord, fill=fill)
+    ctx.close()
+    return q, delp
+
+
+def test_config1_full_step_c48_l64(oracle, case_factory, mode):
+    """BASELINE config 1: C48 L64, 9 tracers, fp64, hord_tr 8 / kord_tr 9: one tracer_2d + one tracer remap (mapn_tracer)."""
+    case = case_factory(48, 64, 9, "float64")
+    ref = oracle.tracer_2d(case, hord=8)
+    got = run_gpu_tracer_2d(case, 8)
+    check_q(got["q"], ref["q"], mode, "float64", bit_exact_expected=False, what="C48 L64 advect")
+    qref, dref = oracle.remap_tracers(got["q"], case.pe, case.ak, case.bk, case.ptop, 9, fill=True)
+    q, delp = _remap_gpu(case, got["q"], 9)
+    sl = slice(NG, -NG)
+    assert np.array_equal(delp[..., sl, sl], dref[..., sl, sl])
+    check_q(q, qref, mode, "float64", bit_exact_expected=False, what="C48 L64 remap")
+
+
+@pytest.mark.parametrize("npz", [6, 127, 128])
+def test_level_count_extremes(oracle, case_factory, npz, mode):
+    """The smallest (6) and largest (128; operational 127) level counts the build supports."""
+    case = case_factory(12, npz, 9, "float64", courant=1.8)
+    ref = oracle.tracer_2d(case, hord=8)
+    got = run_gpu_tracer_2d(case, 8)
+    assert got["nsplt"] == ref["nsplt"] and np.array_equal(got["ksplt"], ref["ksplt"])
+    check_q(got["q"], ref["q"], mode, "float64", bit_exact_expected=False, what=f"npz={npz} advect")
+    qref, dref = oracle.remap_tracers(case.q, case.pe, case.ak, case.bk, case.ptop, 9, fill=True)
+    q, delp = _remap_gpu(case, case.q, 9)
+    sl = slice(NG, -NG)
+    assert np.array_equal(delp[..., sl, sl], dref[..., sl, sl])
+    check_q(q, qref, mode, "float64", bit_exact_expected=False, what=f"npz={npz} remap")
+
+
+@pytest.mark.parametrize("nq", [1, 6, 30])
+def test_tracer_count_extremes(oracle, case_factory, nq, mode):
+    """One tracer (map1_q2 branch of the remap), the smallest mapn_tracer set (6) and the 30-tracer aerosol-suite size."""
+    base = case_factory(12, 16, 9, "float64")
+    reps = -(-nq // 9)
+    q0 = np.ascontiguousarray(np.concatenate([base.q * (1.0 + 0.25 * r) for r in range(reps)], axis=1)[:, :nq])
+    import copy
+    case = copy.copy(base)
+    case.q, case.nq = q0, nq
+    ref = oracle.tracer_2d(case, hord=8)
+    got = run_gpu_tracer_2d(case, 8)
+    check_q(got["q"], ref["q"], mode, "float64", bit_exact_expected=False, what=f"nq={nq} advect")
+    qref, _ = oracle.remap_tracers(q0, case.pe, case.ak, case.bk, case.ptop, 9, fill=True)
+    q, _ = _remap_gpu(case, q0, 9)
+    check_q(q, qref, mode, "float64", bit_exact_expected=(nq <= 5), what=f"nq={nq} remap")
+
+
+def test_q_split_and_no_fill(oracle, case_factory, mode):
+    """q_split /= 0 fixes nsplt (fv_tracer2d.F90:437-441); fill = .false. skips fillz."""
+    case = case_factory(24, 16, 9, "float64", courant=0.7)
+    ref = oracle.tracer_2d(case, hord=8, q_split=3)
+    got = run_gpu_tracer_2d(case, 8, q_split=3)
+    assert got["nsplt"] == ref["nsplt"] == 3
+    check_q(got["q"], ref["q"], mode, "float64", bit_exact_expected=False, what="q_split=3")
+    sl = slice(NG, -NG)
+    assert np.array_equal(got["dp1"][..., sl, sl], ref["dp1"][..., sl, sl])
+    qref, _ = oracle.remap_tracers(case.q, case.pe, case.ak, case.bk, case.ptop, 9, fill=False)
+    q, _ = _remap_gpu(case, case.q, 9, fill=False)
+    check_q(q, qref, mode, "float64", bit_exact_expected=False, what="fill=False")
+
+
+def test_row_granular_mapn_tracer_entry(oracle, case_factory, mode):
+    """fv3t_*_mapn_tracer with the reference's own argument list (fv_mapz.F90:1386-1402), one tile, row by row as the
+    reference's j loop calls it: equals the batched remap of that tile."""
+    case = case_factory(12, 16, 9, "float64")
+    qref, _ = oracle.remap_tracers(case.q, case.pe, case.ak, case.bk, case.ptop, 9, fill=True)
+    n, km, nq = case.n, case.npz, case.nq
+    g = {k: v[:1] for k, v in case.metrics().items()}
+    ctx = TracerContext(n + 1, km, nq, g, dtype=case.dtype, tiles=(1,))
+    ctx.set_vertical(case.ak, case.bk, case.ptop)
+    q1 = np.ascontiguousarray(case.q[0])                      # (nq, km, n+6, n+6) = q1(isd:ied, jsd:jed, km, nq)
+    kord = np.full(nq, 9, dtype=np.int32)
+    for j in range(1, n + 1):
+        pe1 = np.ascontiguousarray(case.pe[0, j, :, 1:-1])    # pe(is:ie, 1:km+1, j) -> (km+1, n)
+        ps = pe1[-1]
+        pe2 = case.ak[:, None] + case.bk[:, None] * ps[None, :]
+        pe2[0], pe2[-1] = case.ptop, ps
+        dp2 = np.ascontiguousarray(np.diff(pe2, axis=0))
+        ctx.mapn_tracer(nq, km, pe1, np.ascontiguousarray(pe2), q1, dp2, kord, j, 1, n, -2, n + 3, -2, n + 3, 0.0, True)
+    ctx.close()
+    sl = slice(NG, -NG)
+    assert np.array_equal(q1[..., sl, sl], qref[0][..., sl, sl])
