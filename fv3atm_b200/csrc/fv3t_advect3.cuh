@@ -268,13 +268,14 @@ template <class P> FV3T_HD void keep_ptr(P*& x) {
 #endif
 }
 
-template <class T> struct Adv3Cta {  // CTA-uniform
+template <class T, int G> struct Adv3Cta {  // CTA-uniform
   int n, npx, nd, i0, nw, gb;
   int levoff, tileoff, mxoff, myoff;  // element offsets of this (tile, level) in the per-level / 2-D / mfx / mfy arrays
-  long qoff;                          // element offset of this (tile, tracer, level) plane of q
+  long qoff[G];                       // element offset of the (tile, tracer, level) plane of q, per tracer of the group
+  bool live[G];                       // tracer iq0 + g exists (the last group of an nq not divisible by G is padded)
 };
 
-template <class T> FV3T_HD bool adv3_make_cta(const Adv3Params<T>& p, int iq, int strip, int lev, Adv3Cta<T>& c) {
+template <class T, int G> FV3T_HD bool adv3_make_cta(const Adv3Params<T>& p, int iqg, int strip, int lev, Adv3Cta<T, G>& c) {
   const int n = p.n, npz = p.npz;
   const int t = lev / npz, kz = lev % npz;
   if (p.it > p.ksplt[kz]) return false;
@@ -290,14 +291,19 @@ template <class T> FV3T_HD bool adv3_make_cta(const Adv3Params<T>& p, int iq, in
   c.tileoff = t * plane;
   c.mxoff = lev * (n + 1) * n;
   c.myoff = lev * n * (n + 1);
-  c.qoff = (((long)t * p.nq + iq) * npz + kz) * (long)plane;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int iq = iqg * G + g;
+    c.live[g] = iq < p.nq;
+    c.qoff[g] = (((long)t * p.nq + (c.live[g] ? iq : p.nq - 1)) * npz + kz) * (long)plane;
+  }
   return true;
 }
 
 // Per-thread constants.  Every thread of the CTA executes every phase unconditionally -- threads outside their role
 // compute on clamped (always valid) addresses and their results are never stored -- because role-dependent early exits
 // made the compiler merge the whole carried state with register moves at every join (a quarter of all executed
-// instructions in the second version, profiles/r01_advect3_v1_opmix.txt).
+// instructions in the second version, profiles/r01_advect3_block_sweep.txt).
 struct Adv3Thr {
   int tid, i;
   int cell;  // this thread owns a compute column of the strip: its flux-form update is stored
@@ -307,7 +313,7 @@ struct Adv3Thr {
   int imy;   // clamped column offset in an mfy row, i - 1 in 0..n-1
 };
 
-template <class T, int OI, int OO> FV3T_HD Adv3Thr adv3_thread(const Adv3Cta<T>& c, int tid) {
+template <class T, int G> FV3T_HD Adv3Thr adv3_thread(const Adv3Cta<T, G>& c, int tid) {
   Adv3Thr t;
   const int n = c.n;
   t.tid = tid;
@@ -327,51 +333,65 @@ template <class T, int OI, int OO> FV3T_HD Adv3Thr adv3_thread(const Adv3Cta<T>&
   return t;
 }
 
-template <class T, int OI, int OO> struct Adv3State {
-  YStream<T, OI> yin;
-  YStream<T, OO> you;
-  T fx2_a, fx2_b, fx2_c;  // inner x flux of this thread's face at rows r-1, r-2, r-3
-  T Fy_prev, fys_prev;    // yfx*fy2 / (fy+fy2)*mfy at the previous y-face
-  T qx, fy2_c, q_o, cyv;  // values of the current row step that cross its barriers
-  // inputs of the phases, each (re)loaded for the NEXT row step at the end of the phase that has just consumed it, so
-  // that every global load has a whole row step of latency tolerance and needs neither a second register nor a move
-  T in_qx, in_qy, in_area_o, in_rry;  // phase 1
+// G tracers of one (tile, level, strip) march in lock-step in one thread: the level fields, their addresses, the row
+// bookkeeping, the upwind selections and the three barriers per row step are paid once per G tracers, and G independent
+// dependency chains hide the FP64 latency.
+template <class T, int OI, int OO, int G> struct Adv3State {
+  struct PerTracer {
+    YStream<T, OI> yin;
+    YStream<T, OO> you;
+    T fx2_a, fx2_b, fx2_c;  // inner x flux of this thread's face at rows r-1, r-2, r-3
+    T Fy_prev, fys_prev;    // yfx*fy2 / (fy+fy2)*mfy at the previous y-face
+    T qx, fy2_c, q_o;       // values of the current row step that cross its barriers
+    T in_qx, in_qy;         // phase-1 input
+    const T* qg;            // this thread's (clamped) column of q, row -2
+    T* qo;
+  } tr[G];
+  T cyv;
+  // tracer-independent inputs of the phases, each (re)loaded for the NEXT row step at the end of the phase that has just
+  // consumed it, so that every global load has a whole row step of latency tolerance and needs neither a second register
+  // nor a move
+  T in_area_o, in_rry;            // phase 1
   Pair<T> in_y2;
-  Pair<T> in_x2r;                     // phase 3
+  Pair<T> in_x2r;                 // phase 3
   T in_cxo, in_mfx;
-  T in_area_r, in_rrx, in_mfy;        // phase 4
+  T in_area_r, in_rrx, in_mfy;    // phase 4
   Pair<T> in_ab;
-  const T* qg;  // this thread's (clamped) column of q, row -2
-  T* qo;
-  T* smt;       // shared memory: this thread's slot of row 0 (rows are SMP apart)
+  T* smt;  // shared memory: this thread's slot of row 0 (rows are SMP apart; tracer g uses rows 6g .. 6g+5)
 };
 
-template <class T, int OI, int OO>
-FV3T_HD void adv3_init(const Adv3Params<T>& p, const Adv3Cta<T>& c, const Adv3Thr& t, T* smem, Adv3State<T, OI, OO>& s) {
-  s.yin.init();
-  s.you.init();
-  s.fx2_a = s.fx2_b = s.fx2_c = T(0);
-  s.Fy_prev = s.fys_prev = T(0);
-  s.qx = s.fy2_c = s.q_o = s.cyv = T(0);
-  s.in_qx = s.in_qy = s.in_area_o = s.in_rry = T(0);
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_init(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, const Adv3Thr& t, T* smem, Adv3State<T, OI, OO, G>& s) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    auto& a = s.tr[g];
+    a.yin.init();
+    a.you.init();
+    a.fx2_a = a.fx2_b = a.fx2_c = T(0);
+    a.Fy_prev = a.fys_prev = T(0);
+    a.qx = a.fy2_c = a.q_o = T(0);
+    a.in_qx = a.in_qy = T(0);
+    a.qg = p.qin + c.qoff[g] + t.pix;
+    a.qo = p.qout + c.qoff[g] + t.pix;
+    keep_ptr(a.qg);
+    keep_ptr(a.qo);
+  }
+  s.cyv = T(0);
+  s.in_area_o = s.in_rry = T(0);
   s.in_y2 = s.in_x2r = s.in_ab = Pair<T>{T(0), T(0)};
   s.in_cxo = s.in_mfx = s.in_area_r = s.in_rrx = s.in_mfy = T(0);
-  s.qg = p.qin + c.qoff + t.pix;
-  s.qo = p.qout + c.qoff + t.pix;
   s.smt = smem + SMPAD + t.tid;  // not made opaque: the compiler must keep seeing a shared-memory address (LDS/STS)
-  keep_ptr(s.qg);
-  keep_ptr(s.qo);
 }
 
-// shared-memory rows (each SMP elements): 0 q of row r, 1 dm/al of row r, 2 q_i of row o, 3 dm/al of row o,
+// shared-memory rows (each SMP elements) of tracer g: 0 q of row r, 1 dm/al of row r, 2 q_i of row o, 3 dm/al of row o,
 // 4 xfx*fx2 of row r, 5 (fx+fx2)*mfx of row o
-#define FV3T_SROW(s, k) ((s).smt + (k) * SMP)
+#define FV3T_SROW(s, g, k) ((s).smt + ((g) * 6 + (k)) * SMP)
 
 FV3T_HD int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // loads for phase 1 of row step r (rows beyond the tile are clamped: their values are never used)
-template <class T, int OI, int OO>
-FV3T_HD void adv3_fetch1(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_fetch1(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd, npx = c.npx;
   r = r > n + 3 ? n + 3 : r;
   const int i = t.i;
@@ -392,16 +412,19 @@ FV3T_HD void adv3_fetch1(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<
     ox = (s1j + 2) * nd + (s1i - i);
     oy = (s2j + 2) * nd + (s2i - i);
   }
-  s.in_qx = s.qg[ox];
-  s.in_qy = s.qg[oy];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    s.tr[g].in_qx = s.tr[g].qg[ox];
+    s.tr[g].in_qy = s.tr[g].qg[oy];
+  }
   s.in_y2 = p.Y2[c.levoff + (cc + 2) * nd + t.pix];
   s.in_area_o = p.area[c.tileoff + (o + 2) * nd + t.pix];
   s.in_rry = p.rry[c.levoff + (o + 2) * nd + t.pix];
 }
 
 // loads for phase 3 of row step r
-template <class T, int OI, int OO>
-FV3T_HD void adv3_fetch3(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_fetch3(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd;
   r = r > n + 3 ? n + 3 : r;
   const int o = clampi(r - 3, 1, n);
@@ -411,8 +434,8 @@ FV3T_HD void adv3_fetch3(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<
 }
 
 // loads for phase 4 of row step r
-template <class T, int OI, int OO>
-FV3T_HD void adv3_fetch4(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_fetch4(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd;
   r = r > n + 3 ? n + 3 : r;
   const int cc = clampi(r - 2, 1, n + 1), o = clampi(r - 3, 1, n);
@@ -423,110 +446,126 @@ FV3T_HD void adv3_fetch4(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<
 }
 
 // phase 1: inner y sweep (flux at y-face c = r-2), q_i of row o = r-3, rows of q / q_i to shared memory
-template <class T, int OI, int OO>
-FV3T_HD void adv3_phase1(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_phase1(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd;
   const int cc = r - 2;
   const bool c_ok = cc >= 1 && cc <= n + 1;
-  const T qx = s.in_qx, qy = s.in_qy;
   const T cyv = c_ok ? s.in_y2.a : T(0), yfv = c_ok ? s.in_y2.b : T(0);
   const T* dya = p.dya + c.tileoff + t.pix;
   auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
-  T q_o;
-  const T fy2_c = s.yin.push(cc, qy, cyv, c.npx, p.lim_fac, met_y, q_o);
-  const T Fy_c = yfv * fy2_c;
-  const T qi = (q_o * s.in_area_o + s.Fy_prev - Fy_c) * s.in_rry;  // only rows o = 1..n are consumed
-  s.Fy_prev = Fy_c;
-  s.fy2_c = fy2_c;
-  s.q_o = q_o;
-  s.qx = qx;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    auto& a = s.tr[g];
+    const T qx = a.in_qx, qy = a.in_qy;
+    T q_o;
+    const T fy2_c = a.yin.push(cc, qy, cyv, c.npx, p.lim_fac, met_y, q_o);
+    const T Fy_c = yfv * fy2_c;
+    const T qi = (q_o * s.in_area_o + a.Fy_prev - Fy_c) * s.in_rry;  // only rows o = 1..n are consumed
+    a.Fy_prev = Fy_c;
+    a.fy2_c = fy2_c;
+    a.q_o = q_o;
+    a.qx = qx;
+    FV3T_SROW(s, g, 0)[0] = qx;
+    FV3T_SROW(s, g, 2)[0] = qi;
+  }
   s.cyv = cyv;
-  FV3T_SROW(s, 0)[0] = qx;
-  FV3T_SROW(s, 2)[0] = qi;
-  adv3_fetch1<T, OI, OO>(p, c, s, t, r + 1);
+  adv3_fetch1<T, OI, OO, G>(p, c, s, t, r + 1);
 }
 
 // phase 2: dm (ORD >= 7) or al (ORD < 7) of row r (inner x sweep) and of row o (outer x sweep on q_i)
-template <class T, int OI, int OO>
-FV3T_HD void adv3_phase2(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_phase2(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int nd = c.nd;
   const int o = clampi(r - 3, 1, c.n);
   const int i = t.i;
-  const T* sqa = FV3T_SROW(s, 0) - i;  // indexable by the global column
-  const T* sqb = FV3T_SROW(s, 2) - i;
   const T* dxa = p.dxa + c.tileoff + 2;
-  auto qa = [&](int gi) -> T { return sqa[gi]; };
-  auto qb = [&](int gi) -> T { return sqb[gi]; };
   auto dxa_r = [&](int gi) -> T { return dxa[(r + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
-  FV3T_SROW(s, 1)[0] = ppm_pre<T, OI>(i, c.npx, qa, dxa_r);
-  FV3T_SROW(s, 3)[0] = ppm_pre<T, OO>(i, c.npx, qb, dxa_o);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const T* sqa = FV3T_SROW(s, g, 0) - i;  // indexable by the global column
+    const T* sqb = FV3T_SROW(s, g, 2) - i;
+    auto qa = [&](int gi) -> T { return sqa[gi]; };
+    auto qb = [&](int gi) -> T { return sqb[gi]; };
+    FV3T_SROW(s, g, 1)[0] = ppm_pre<T, OI>(i, c.npx, qa, dxa_r);
+    FV3T_SROW(s, g, 3)[0] = ppm_pre<T, OO>(i, c.npx, qb, dxa_o);
+  }
 }
 
 // phase 3: x-face fluxes: inner sweep of row r (-> xfx*fx2), outer sweep of row o (-> (fx+fx2)*mfx)
-template <class T, int OI, int OO>
-FV3T_HD void adv3_phase3(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_phase3(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int nd = c.nd;
   const int o = clampi(r - 3, 1, c.n);
   const int i = t.i;
-  const T *sqa = FV3T_SROW(s, 0) - i, *sda = FV3T_SROW(s, 1) - i, *sqb = FV3T_SROW(s, 2) - i, *sdb = FV3T_SROW(s, 3) - i;
   const T* dxa = p.dxa + c.tileoff + 2;
-  auto qa = [&](int gi) -> T { return sqa[gi]; };
-  auto aa = [&](int gi) -> T { return sda[gi]; };
-  auto qb = [&](int gi) -> T { return sqb[gi]; };
-  auto ab = [&](int gi) -> T { return sdb[gi]; };
   auto dxa_r = [&](int gi) -> T { return dxa[(r + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
-  const T fx2 = xface_flux<T, OI>(i, s.in_x2r.a, c.npx, p.lim_fac, qa, aa, dxa_r);
-  FV3T_SROW(s, 4)[0] = s.in_x2r.b * fx2;
-  const T fxo = xface_flux<T, OO>(i, s.in_cxo, c.npx, p.lim_fac, qb, ab, dxa_o);
-  FV3T_SROW(s, 5)[0] = (fxo + s.fx2_c) * s.in_mfx;
-  s.fx2_c = s.fx2_b;
-  s.fx2_b = s.fx2_a;
-  s.fx2_a = fx2;
-  adv3_fetch3<T, OI, OO>(p, c, s, t, r + 1);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    auto& a = s.tr[g];
+    const T *sqa = FV3T_SROW(s, g, 0) - i, *sda = FV3T_SROW(s, g, 1) - i, *sqb = FV3T_SROW(s, g, 2) - i, *sdb = FV3T_SROW(s, g, 3) - i;
+    auto qa = [&](int gi) -> T { return sqa[gi]; };
+    auto aa = [&](int gi) -> T { return sda[gi]; };
+    auto qb = [&](int gi) -> T { return sqb[gi]; };
+    auto ab = [&](int gi) -> T { return sdb[gi]; };
+    const T fx2 = xface_flux<T, OI>(i, s.in_x2r.a, c.npx, p.lim_fac, qa, aa, dxa_r);
+    FV3T_SROW(s, g, 4)[0] = s.in_x2r.b * fx2;
+    const T fxo = xface_flux<T, OO>(i, s.in_cxo, c.npx, p.lim_fac, qb, ab, dxa_o);
+    FV3T_SROW(s, g, 5)[0] = (fxo + a.fx2_c) * s.in_mfx;
+    a.fx2_c = a.fx2_b;
+    a.fx2_b = a.fx2_a;
+    a.fx2_a = fx2;
+  }
+  adv3_fetch3<T, OI, OO, G>(p, c, s, t, r + 1);
 }
 
 // phase 4: q_j of row r, outer y sweep (flux at y-face c), flux-form update of row o
-template <class T, int OI, int OO>
-FV3T_HD void adv3_phase4(const Adv3Params<T>& p, const Adv3Cta<T>& c, Adv3State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int G>
+FV3T_HD void adv3_phase4(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3State<T, OI, OO, G>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd;
   const int cc = r - 2, o = r - 3;
   const bool o_ok = o >= 1 && o <= n;
   const bool c_ok = cc >= 1 && cc <= n + 1;
-  const T* sf1 = FV3T_SROW(s, 4);
-  const T* sft = FV3T_SROW(s, 5);
-  const T qj = (s.qx * s.in_area_r + sf1[0] - sf1[1]) * s.in_rrx;
   const T* dya = p.dya + c.tileoff + t.pix;
   auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
-  T dummy;
-  const T fyo_c = s.you.push(cc, qj, s.cyv, c.npx, p.lim_fac, met_y, dummy);
-  const T fys_c = c_ok ? (fyo_c + s.fy2_c) * s.in_mfy : T(0);
-  const T qnew = s.q_o * s.in_ab.a + (sft[0] - sft[1] + s.fys_prev - fys_c) * s.in_ab.b;
-  if (o_ok && t.cell) s.qo[(o + 2) * nd] = qnew;
-  s.fys_prev = fys_c;
-  adv3_fetch4<T, OI, OO>(p, c, s, t, r + 1);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    auto& a = s.tr[g];
+    const T* sf1 = FV3T_SROW(s, g, 4);
+    const T* sft = FV3T_SROW(s, g, 5);
+    const T qj = (a.qx * s.in_area_r + sf1[0] - sf1[1]) * s.in_rrx;
+    T dummy;
+    const T fyo_c = a.you.push(cc, qj, s.cyv, c.npx, p.lim_fac, met_y, dummy);
+    const T fys_c = c_ok ? (fyo_c + a.fy2_c) * s.in_mfy : T(0);
+    const T qnew = a.q_o * s.in_ab.a + (sft[0] - sft[1] + a.fys_prev - fys_c) * s.in_ab.b;
+    if (o_ok && t.cell && c.live[g]) a.qo[(o + 2) * nd] = qnew;
+    a.fys_prev = fys_c;
+  }
+  adv3_fetch4<T, OI, OO, G>(p, c, s, t, r + 1);
 }
 
 #ifdef __CUDACC__
-template <class T, int OI, int OO, int MINB> __global__ void __launch_bounds__(256, MINB) k_advect3(const __grid_constant__ Adv3Params<T> p) {
-  __shared__ __align__(16) T smem3[6 * SMP];
-  Adv3Cta<T> c;
-  if (!adv3_make_cta<T>(p, blockIdx.x, blockIdx.y, blockIdx.z, c)) return;
-  const Adv3Thr t = adv3_thread<T, OI, OO>(c, threadIdx.x);
-  Adv3State<T, OI, OO> s;
-  adv3_init<T, OI, OO>(p, c, t, smem3, s);
-  adv3_fetch1<T, OI, OO>(p, c, s, t, -2);
-  adv3_fetch3<T, OI, OO>(p, c, s, t, -2);
-  adv3_fetch4<T, OI, OO>(p, c, s, t, -2);
+template <class T, int OI, int OO, int G, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_advect3(const __grid_constant__ Adv3Params<T> p) {
+  __shared__ __align__(16) T smem3[6 * G * SMP];
+  Adv3Cta<T, G> c;
+  if (!adv3_make_cta<T, G>(p, blockIdx.x, blockIdx.y, blockIdx.z, c)) return;
+  const Adv3Thr t = adv3_thread<T, G>(c, threadIdx.x);
+  Adv3State<T, OI, OO, G> s;
+  adv3_init<T, OI, OO, G>(p, c, t, smem3, s);
+  adv3_fetch1<T, OI, OO, G>(p, c, s, t, -2);
+  adv3_fetch3<T, OI, OO, G>(p, c, s, t, -2);
+  adv3_fetch4<T, OI, OO, G>(p, c, s, t, -2);
   for (int r = -2; r <= c.n + 3; ++r) {
-    adv3_phase1<T, OI, OO>(p, c, s, t, r);
+    adv3_phase1<T, OI, OO, G>(p, c, s, t, r);
     __syncthreads();
-    adv3_phase2<T, OI, OO>(p, c, s, t, r);
+    adv3_phase2<T, OI, OO, G>(p, c, s, t, r);
     __syncthreads();
-    adv3_phase3<T, OI, OO>(p, c, s, t, r);
+    adv3_phase3<T, OI, OO, G>(p, c, s, t, r);
     __syncthreads();
-    adv3_phase4<T, OI, OO>(p, c, s, t, r);
+    adv3_phase4<T, OI, OO, G>(p, c, s, t, r);
   }
 }
 #endif

@@ -27,12 +27,16 @@ template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cud
 template <class T, int OI, int OO> static cudaError_t launch3(Adv3Params<T>& p, int NT, cudaStream_t stream) {
   p.W = NT - 6;
   const int strips = (p.n + p.W - 1) / p.W;
-  dim3 grid(p.nq, strips, p.ntiles * p.npz);
-  static const int minb = getenv("FV3T_ADV_MINB") ? atoi(getenv("FV3T_ADV_MINB")) : 2;  // tuning knob: register cap 128 (2) / 255 (1)
-  if (minb == 1)
-    k_advect3<T, OI, OO, 1><<<grid, NT, 0, stream>>>(p);
-  else
-    k_advect3<T, OI, OO, 2><<<grid, NT, 0, stream>>>(p);
+  // tracers per thread (tuning knob).  B200, C768: G = 1 131 ms, G = 2 177 ms, G = 3 211 ms (255 registers -> 8 warps/SM):
+  // sharing the level fields does not pay for the lost occupancy (profiles/r01_advect3_block_sweep.txt)
+  static const int grp = getenv("FV3T_ADV_G") ? atoi(getenv("FV3T_ADV_G")) : 1;
+  if (grp == 2) {
+    dim3 grid((p.nq + 1) / 2, strips, p.ntiles * p.npz);
+    k_advect3<T, OI, OO, 2, 1><<<grid, NT, 0, stream>>>(p);
+  } else {
+    dim3 grid(p.nq, strips, p.ntiles * p.npz);
+    k_advect3<T, OI, OO, 1, 2><<<grid, NT, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
@@ -57,7 +61,13 @@ template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaSt
 
 template <class T, int AK> static cudaError_t launch_remap3(const Remap3Params<T>& p, cudaStream_t stream) {
   dim3 grid(p.nq, (p.n * p.n + 127) / 128, p.ntiles);
-  k_remap3<T, AK, true, 128><<<grid, 128, 0, stream>>>(p);
+  static const int minb = getenv("FV3T_REMAP_MINB") ? atoi(getenv("FV3T_REMAP_MINB")) : 4;  // tuning knob: 4 -> 128 regs, 5 -> 96, 6 -> 80
+  if (minb == 5)
+    k_remap3<T, AK, true, 128, 5><<<grid, 128, 0, stream>>>(p);
+  else if (minb == 6)
+    k_remap3<T, AK, true, 128, 6><<<grid, 128, 0, stream>>>(p);
+  else
+    k_remap3<T, AK, true, 128, 4><<<grid, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -389,7 +389,7 @@ template <class T> __global__ void __launch_bounds__(128) k_remap_coef3(const Re
   if (c >= cols) return;
   remap_coef_column<T>(p, blockIdx.y, c % p.n + 1, c / p.n + 1);
 }
-template <class T, int AK, bool MAPN, int KM> __global__ void __launch_bounds__(128, 4) k_remap3(const Remap3Params<T> p) {
+template <class T, int AK, bool MAPN, int KM, int MINB> __global__ void __launch_bounds__(128, MINB) k_remap3(const Remap3Params<T> p) {
   // ak, bk in shared memory: pe2(k) = ak + bk*ps sits on the dependent path of the target-layer loop
   __shared__ T s_ak[KM + 1], s_bk[KM + 1];
   for (int k = threadIdx.x; k <= p.km; k += blockDim.x) {

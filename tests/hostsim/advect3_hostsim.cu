@@ -10,33 +10,47 @@
 
 using namespace fv3t;
 
-template <class T, int OI, int OO>
-static void run_substep(const Adv3Params<T>& p, int NT) {
+static int g_group = 1;  // tracers per simulated thread (set by the test through hostsim_set_group)
+
+template <class T, int OI, int OO, int G>
+static void run_substep_g(const Adv3Params<T>& p, int NT) {
   const int n = p.n;
   const int strips = (n + p.W - 1) / p.W;
-  std::vector<T> smem(6 * (size_t)SMP);
-  std::vector<Adv3State<T, OI, OO>> st(NT);
+  std::vector<T> smem(6 * G * (size_t)SMP);
+  std::vector<Adv3State<T, OI, OO, G>> st(NT);
   std::vector<Adv3Thr> th(NT);
   for (int lev = 0; lev < p.ntiles * p.npz; ++lev)
     for (int strip = 0; strip < strips; ++strip)
-      for (int iq = 0; iq < p.nq; ++iq) {
-        Adv3Cta<T> c;
-        if (!adv3_make_cta<T>(p, iq, strip, lev, c)) continue;
+      for (int iqg = 0; iqg < (p.nq + G - 1) / G; ++iqg) {
+        Adv3Cta<T, G> c;
+        if (!adv3_make_cta<T, G>(p, iqg, strip, lev, c)) continue;
         for (int tid = 0; tid < NT; ++tid) {
-          th[tid] = adv3_thread<T, OI, OO>(c, tid);
-          adv3_init<T, OI, OO>(p, c, th[tid], smem.data(), st[tid]);
-          adv3_fetch1<T, OI, OO>(p, c, st[tid], th[tid], -2);
-          adv3_fetch3<T, OI, OO>(p, c, st[tid], th[tid], -2);
-          adv3_fetch4<T, OI, OO>(p, c, st[tid], th[tid], -2);
+          th[tid] = adv3_thread<T, G>(c, tid);
+          adv3_init<T, OI, OO, G>(p, c, th[tid], smem.data(), st[tid]);
+          adv3_fetch1<T, OI, OO, G>(p, c, st[tid], th[tid], -2);
+          adv3_fetch3<T, OI, OO, G>(p, c, st[tid], th[tid], -2);
+          adv3_fetch4<T, OI, OO, G>(p, c, st[tid], th[tid], -2);
         }
         for (int r = -2; r <= n + 3; ++r) {
-          for (int tid = 0; tid < NT; ++tid) adv3_phase1<T, OI, OO>(p, c, st[tid], th[tid], r);
-          for (int tid = 0; tid < NT; ++tid) adv3_phase2<T, OI, OO>(p, c, st[tid], th[tid], r);
-          for (int tid = 0; tid < NT; ++tid) adv3_phase3<T, OI, OO>(p, c, st[tid], th[tid], r);
-          for (int tid = 0; tid < NT; ++tid) adv3_phase4<T, OI, OO>(p, c, st[tid], th[tid], r);
+          for (int tid = 0; tid < NT; ++tid) adv3_phase1<T, OI, OO, G>(p, c, st[tid], th[tid], r);
+          for (int tid = 0; tid < NT; ++tid) adv3_phase2<T, OI, OO, G>(p, c, st[tid], th[tid], r);
+          for (int tid = 0; tid < NT; ++tid) adv3_phase3<T, OI, OO, G>(p, c, st[tid], th[tid], r);
+          for (int tid = 0; tid < NT; ++tid) adv3_phase4<T, OI, OO, G>(p, c, st[tid], th[tid], r);
         }
       }
 }
+
+template <class T, int OI, int OO>
+static void run_substep(const Adv3Params<T>& p, int NT) {
+  if (g_group == 2)
+    run_substep_g<T, OI, OO, 2>(p, NT);
+  else if (g_group == 3)
+    run_substep_g<T, OI, OO, 3>(p, NT);
+  else
+    run_substep_g<T, OI, OO, 1>(p, NT);
+}
+
+extern "C" void hostsim_set_group(int g) { g_group = g; }
 
 template <class T> static int dispatch(const Adv3Params<T>& p, int hord, int NT) {
   switch (hord) {

@@ -32,7 +32,8 @@ def sim():
     return C.CDLL(so)
 
 
-def run_sim(sim, case, hord, ref, NT, lim_fac=1.0):
+def run_sim(sim, case, hord, ref, NT, lim_fac=1.0, group=1):
+    sim.hostsim_set_group(int(group))
     sfx, ct = ("f64", C.c_double) if case.dtype == np.float64 else ("f32", C.c_float)
     g = case.metrics()
     out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
@@ -78,6 +79,17 @@ def test_discontinuous_schemes_stay_on_the_strict_path(sim, oracle, case_factory
     smooth = [i for i in range(9) if i != 2]
     assert nd[smooth].max() <= 1e-12, nd
     assert nd[2] > 1e-9, nd
+
+
+@pytest.mark.parametrize("group", [2, 3])
+def test_tracer_groups_per_thread(sim, oracle, case_factory, group):
+    """G tracers marching in one thread (9 = 4*2+1 and 3*3: the padded last group must not store)."""
+    case = case_factory(12, 8, 9, "float64", courant=1.8)
+    ref = oracle.tracer_2d(case, hord=8)
+    got = run_sim(sim, case, 8, ref, NT=32, group=group)
+    one = run_sim(sim, case, 8, ref, NT=32, group=1)
+    assert norm_diff(got["q"], ref["q"]).max() <= 1e-12
+    assert np.array_equal(got["q"], one["q"])
 
 
 @pytest.mark.parametrize("NT", [32, 64])
