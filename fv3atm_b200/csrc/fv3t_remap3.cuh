@@ -203,7 +203,9 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   int k = 1;
   T pe2k = PE2(1), pe2k1 = PE2(2);
   T dpk = pe2k1 - pe2k, dpk_m1 = T(0), dpk_m2 = T(0);
-  T rdpk = R2[0];
+  // 1/dp2 of the current target layer and of the next two: the load sits two target layers ahead of its use (it was the
+  // single largest stall site of the first version: 24 % of all stall samples on `qsum * rdpk`)
+  T rdpk = R2[0], rdp_n1 = R2[plane], rdp_n2 = R2[2 * plane];
   bool started = false;
 
   auto finalize = [&](int kk, T x, T dpkk) {
@@ -264,7 +266,9 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
       dpk_m2 = dpk_m1;
       dpk_m1 = dpk;
       dpk = pe2k1 - pe2k;
-      rdpk = R2[(long)(k - 1) * plane];
+      rdpk = rdp_n1;
+      rdp_n1 = rdp_n2;
+      rdp_n2 = R2[(long)(k + 1 <= km - 1 ? k + 1 : km - 1) * plane];
     }
   };
 
