@@ -342,7 +342,7 @@ template <class T, int OI, int OO, int G> struct Adv3State {
     YStream<T, OO> you;
     T fx2_a, fx2_b, fx2_c;  // inner x flux of this thread's face at rows r-1, r-2, r-3
     T Fy_prev, fys_prev;    // yfx*fy2 / (fy+fy2)*mfy at the previous y-face
-    T qx, fy2_c, q_o;       // values of the current row step that cross its barriers
+    T fy2_c;                // inner y flux of the current row step (crosses its barriers)
     T in_qx, in_qy;         // phase-1 input
     const T* qg;            // this thread's (clamped) column of q, row -2
     T* qo;
@@ -369,7 +369,7 @@ FV3T_HD void adv3_init(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, const Adv
     a.you.init();
     a.fx2_a = a.fx2_b = a.fx2_c = T(0);
     a.Fy_prev = a.fys_prev = T(0);
-    a.qx = a.fy2_c = a.q_o = T(0);
+    a.fy2_c = T(0);
     a.in_qx = a.in_qy = T(0);
     a.qg = p.qin + c.qoff[g] + t.pix;
     a.qo = p.qout + c.qoff[g] + t.pix;
@@ -388,6 +388,16 @@ FV3T_HD void adv3_init(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, const Adv
 #define FV3T_SROW(s, g, k) ((s).smt + ((g) * 6 + (k)) * SMP)
 
 FV3T_HD int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// Keeps the re-loads of a phase's inputs BEHIND the last use of their previous values.  Without it the scheduler hoists
+// the loads into the phase, has to give them fresh registers, and copies them into the loop-carried registers at the loop
+// back-edge -- a register move that waits for the load right away and so defeats the one-row-step latency tolerance
+// (12 % of all stall samples sat on that move, profiles/r01_advect3_c384_ncu.txt).
+FV3T_HD void load_fence() {
+#ifdef __CUDA_ARCH__
+  asm volatile("" ::: "memory");
+#endif
+}
 
 // loads for phase 1 of row step r (rows beyond the tile are clamped: their values are never used)
 template <class T, int OI, int OO, int G>
@@ -464,12 +474,11 @@ FV3T_HD void adv3_phase1(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3Sta
     const T qi = (q_o * s.in_area_o + a.Fy_prev - Fy_c) * s.in_rry;  // only rows o = 1..n are consumed
     a.Fy_prev = Fy_c;
     a.fy2_c = fy2_c;
-    a.q_o = q_o;
-    a.qx = qx;
     FV3T_SROW(s, g, 0)[0] = qx;
     FV3T_SROW(s, g, 2)[0] = qi;
   }
   s.cyv = cyv;
+  load_fence();
   adv3_fetch1<T, OI, OO, G>(p, c, s, t, r + 1);
 }
 
@@ -518,6 +527,7 @@ FV3T_HD void adv3_phase3(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3Sta
     a.fx2_b = a.fx2_a;
     a.fx2_a = fx2;
   }
+  load_fence();
   adv3_fetch3<T, OI, OO, G>(p, c, s, t, r + 1);
 }
 
@@ -535,14 +545,20 @@ FV3T_HD void adv3_phase4(const Adv3Params<T>& p, const Adv3Cta<T, G>& c, Adv3Sta
     auto& a = s.tr[g];
     const T* sf1 = FV3T_SROW(s, g, 4);
     const T* sft = FV3T_SROW(s, g, 5);
-    const T qj = (a.qx * s.in_area_r + sf1[0] - sf1[1]) * s.in_rrx;
+    // q(i, r) comes back from its shared-memory row (intact until phase 1 of the next row step) and q(i, o) from the inner
+    // y stream's window (after the push of cell c its qm2 is q(c-1) = q(o)): carrying them in registers made the compiler
+    // copy the freshly prefetched q at the loop back-edge, a move that waited for the load at once (12 % of all stalls)
+    const T qx = FV3T_SROW(s, g, 0)[0];
+    const T q_o = a.yin.qm2;
+    const T qj = (qx * s.in_area_r + sf1[0] - sf1[1]) * s.in_rrx;
     T dummy;
     const T fyo_c = a.you.push(cc, qj, s.cyv, c.npx, p.lim_fac, met_y, dummy);
     const T fys_c = c_ok ? (fyo_c + a.fy2_c) * s.in_mfy : T(0);
-    const T qnew = a.q_o * s.in_ab.a + (sft[0] - sft[1] + a.fys_prev - fys_c) * s.in_ab.b;
+    const T qnew = q_o * s.in_ab.a + (sft[0] - sft[1] + a.fys_prev - fys_c) * s.in_ab.b;
     if (o_ok && t.cell && c.live[g]) a.qo[(o + 2) * nd] = qnew;
     a.fys_prev = fys_c;
   }
+  load_fence();
   adv3_fetch4<T, OI, OO, G>(p, c, s, t, r + 1);
 }
 
