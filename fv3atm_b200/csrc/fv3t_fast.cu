@@ -24,12 +24,33 @@ template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cud
   return cudaGetLastError();
 }
 
+template <class T, int OI, int OO, int NTC, int MINB> static cudaError_t launch4(const Adv3Params<T>& p, int NT, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)Adv4Layout<NTC>::TOTAL * sizeof(T);
+  if (smem > 48 * 1024) {
+    static bool once = false;
+    if (!once) {
+      cudaError_t e = cudaFuncSetAttribute(k_advect4<T, OI, OO, NTC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      once = true;
+    }
+  }
+  k_advect4<T, OI, OO, NTC, MINB><<<grid, NT, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 template <class T, int OI, int OO> static cudaError_t launch3(Adv3Params<T>& p, int NT, cudaStream_t stream) {
   p.W = NT - 6;
   const int strips = (p.n + p.W - 1) / p.W;
-  // tracers per thread (tuning knob).  B200, C768: G = 1 131 ms, G = 2 177 ms, G = 3 211 ms (255 registers -> 8 warps/SM):
+  // FV3T_ADV_RING=0 selects the register-prefetch kernel (k_advect3); default: the asynchronous-copy ring (k_advect4)
+  static const int ring = getenv("FV3T_ADV_RING") ? atoi(getenv("FV3T_ADV_RING")) : 1;
+  // tracers per thread of k_advect3 (tuning knob).  B200, C768: G = 1 131 ms, G = 2 177 ms, G = 3 211 ms (255 registers -> 8 warps/SM):
   // sharing the level fields does not pay for the lost occupancy (profiles/r01_advect3_block_sweep.txt)
   static const int grp = getenv("FV3T_ADV_G") ? atoi(getenv("FV3T_ADV_G")) : 1;
+  if (ring) {
+    dim3 grid(p.nq, strips, p.ntiles * p.npz);
+    if (NT <= 64) return launch4<T, OI, OO, 64, 8>(p, NT, grid, stream);
+    return launch4<T, OI, OO, 256, 2>(p, NT, grid, stream);
+  }
   if (grp == 2) {
     dim3 grid((p.nq + 1) / 2, strips, p.ntiles * p.npz);
     k_advect3<T, OI, OO, 2, 1><<<grid, NT, 0, stream>>>(p);

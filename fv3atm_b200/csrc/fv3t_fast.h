@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "fv3t_advect3.cuh"
+#include "fv3t_advect4.cuh"
 #include "fv3t_remap3.cuh"
 
 namespace fv3t {

@@ -4,9 +4,10 @@
 // fv3atm_b200/ links this.  Host orchestration mirrors Impl<T>::tracer_2d_resident of fv3t_api.cu (fast mode).
 #include <cstdint>
 #include <cstring>
+#include <cstdint>
 #include <vector>
 
-#include "../../fv3atm_b200/csrc/fv3t_advect3.cuh"
+#include "../../fv3atm_b200/csrc/fv3t_advect4.cuh"
 
 using namespace fv3t;
 
@@ -40,9 +41,44 @@ static void run_substep_g(const Adv3Params<T>& p, int NT) {
       }
 }
 
+// the asynchronous-copy ring variant (k_advect4): copies complete immediately on the host
+template <class T, int OI, int OO>
+static void run_substep_ring(const Adv3Params<T>& p, int NT) {
+  constexpr int NTC = 256;
+  const int n = p.n;
+  const int strips = (n + p.W - 1) / p.W;
+  std::vector<T> smem(Adv4Layout<NTC>::TOTAL + 2);
+  T* sm = smem.data() + (((uintptr_t)smem.data() & 15) ? 1 : 0);  // 16-byte aligned like the device's shared memory
+  std::vector<Adv4State<T, OI, OO, NTC>> st(NT);
+  std::vector<Adv3Thr> th(NT);
+  for (int lev = 0; lev < p.ntiles * p.npz; ++lev)
+    for (int strip = 0; strip < strips; ++strip)
+      for (int iq = 0; iq < p.nq; ++iq) {
+        Adv3Cta<T, 1> c;
+        if (!adv3_make_cta<T, 1>(p, iq, strip, lev, c)) continue;
+        for (int tid = 0; tid < NT; ++tid) {
+          th[tid] = adv3_thread<T, 1>(c, tid);
+          adv4_init<T, OI, OO, NTC>(p, c, th[tid], sm, st[tid]);
+          adv4_issue<T, OI, OO, NTC>(p, c, st[tid], th[tid], -2, 0);
+        }
+        for (int r = -2; r <= n + 3; ++r) {
+          const int d = (r + 2) & 1;
+          for (int tid = 0; tid < NT; ++tid) {
+            adv4_issue<T, OI, OO, NTC>(p, c, st[tid], th[tid], r + 1, d ^ 1);
+            adv4_phase1<T, OI, OO, NTC>(p, c, st[tid], th[tid], r, d);
+          }
+          for (int tid = 0; tid < NT; ++tid) adv4_phase2<T, OI, OO, NTC>(p, c, st[tid], th[tid], r, d);
+          for (int tid = 0; tid < NT; ++tid) adv4_phase3<T, OI, OO, NTC>(p, c, st[tid], th[tid], r, d);
+          for (int tid = 0; tid < NT; ++tid) adv4_phase4<T, OI, OO, NTC>(p, c, st[tid], th[tid], r, d);
+        }
+      }
+}
+
 template <class T, int OI, int OO>
 static void run_substep(const Adv3Params<T>& p, int NT) {
-  if (g_group == 2)
+  if (g_group == 4)
+    run_substep_ring<T, OI, OO>(p, NT);
+  else if (g_group == 2)
     run_substep_g<T, OI, OO, 2>(p, NT);
   else if (g_group == 3)
     run_substep_g<T, OI, OO, 3>(p, NT);

@@ -24,7 +24,7 @@ def sim():
     so = os.path.join(SIM, "libhostsim_advect3.so")
     src = os.path.join(SIM, "advect3_hostsim.cu")
     csrc = os.path.join(HERE, "..", "fv3atm_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fv3t_advect3.cuh", "fv3t_advect2.cuh", "fv3t_advect.cuh", "fv3t_ppm.cuh",
+    deps = [src] + [os.path.join(csrc, f) for f in ("fv3t_advect4.cuh", "fv3t_advect3.cuh", "fv3t_advect2.cuh", "fv3t_advect.cuh", "fv3t_ppm.cuh",
                                                      "fv3t_common.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["nvcc", "-x", "cu", "-O2", "-std=c++17", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
@@ -79,6 +79,20 @@ def test_discontinuous_schemes_stay_on_the_strict_path(sim, oracle, case_factory
     smooth = [i for i in range(9) if i != 2]
     assert nd[smooth].max() <= 1e-12, nd
     assert nd[2] > 1e-9, nd
+
+
+@pytest.mark.parametrize("hord", [8, 10, 13])
+@pytest.mark.parametrize("courant", [0.7, 1.8])
+def test_async_ring_variant_equals_register_prefetch_variant(sim, oracle, case_factory, hord, courant):
+    """k_advect4 (inputs staged through the cp.async ring; the product default) performs the same arithmetic as
+    k_advect3: identical bits in the host simulation, and within the bar of the oracle."""
+    case = case_factory(20, 8, 9, "float64", courant=courant)
+    ref = oracle.tracer_2d(case, hord=hord)
+    ring = run_sim(sim, case, hord, ref, NT=32, group=4)
+    regs = run_sim(sim, case, hord, ref, NT=32, group=1)
+    assert np.array_equal(ring["q"], regs["q"])
+    if hord != 10:
+        assert norm_diff(ring["q"], ref["q"]).max() <= 1e-12
 
 
 @pytest.mark.parametrize("group", [2, 3])
