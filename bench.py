@@ -251,7 +251,8 @@ def main():
         adv_avg = adv_ms / max(adv_n, 1)
         rm_avg = rm_ms / max(rm_n, 1)
         strict = os.environ.get("FV3T_STRICT", "0") not in ("", "0")
-        names = {"advect": "k_advect2" if strict else "k_advect3", "remap": "k_remap2" if strict else "k_remap3"}
+        ring = os.environ.get("FV3T_ADV_RING", "1") not in ("", "0")
+        names = {"advect": "k_advect2" if strict else ("k_advect4" if ring else "k_advect3"), "remap": "k_remap2" if strict else "k_remap3"}
         dom = "advect" if adv_ms >= rm_ms else "remap"
         kern = names[dom]
         a_bytes, a_ms = (adv_bytes, adv_avg) if dom == "advect" else (rm_bytes, rm_avg)

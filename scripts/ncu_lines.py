@@ -13,7 +13,10 @@ for r in rows:
     if len(r) >= 2 and r[0] == "File Path":
         cur_file = r[1].split("/")[-1]
     elif len(r) > 8 and r[0].isdigit():
-        n = int(r[7] or 0); st = int(r[4] or 0)
+        try:
+            n = int(r[7] or 0); st = int(r[4] or 0)
+        except ValueError:
+            continue
         agg.append((n, st, cur_file, int(r[0]), r[1].strip()[:110])); tot += n
 agg.sort(reverse=True)
 print(f"total warp-instr {tot:.4g} -> {tot*32/div:.1f} per unit")
