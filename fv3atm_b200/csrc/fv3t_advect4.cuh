@@ -30,6 +30,12 @@ FV3T_HD void async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
 }
+// wait until at most N of the most recently committed copy groups of this thread are still in flight
+template <int N> FV3T_HD void async_wait_pending() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 FV3T_HD void async_wait_all() {
 #ifdef __CUDA_ARCH__
   asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -15,7 +15,7 @@
 // Results agree with the FMA-free oracle to ~1e-15 normalised on smooth data (the 1e-12 bar is asserted in the tests); the
 // strict kernel (fv3t_remap2.cuh, FV3T_STRICT=1) stays bit-identical.  Tracer sets with mixed kord use the strict kernel.
 #pragma once
-#include "fv3t_advect3.cuh"
+#include "fv3t_advect4.cuh"
 #include "fv3t_remap2.cuh"
 
 namespace fv3t {
@@ -89,7 +89,7 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
 
 // ---- one column of one tracer; AK = abs(kord) -----------------------------------------------------------------------------
 template <class T, int AK, bool MAPN, int KM>
-FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp, int t, int i, int j, int iq) {
+FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp, T* ring, int rstride, int t, int i, int j, int iq) {
   const int n = p.n, km = p.km;
   const long nd = n + 6, plane = nd * nd;
   const T r3 = K<T>::r3(), r23 = K<T>::r23();
@@ -203,9 +203,20 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   int k = 1;
   T pe2k = PE2(1), pe2k1 = PE2(2);
   T dpk = pe2k1 - pe2k, dpk_m1 = T(0), dpk_m2 = T(0);
-  // 1/dp2 of the current target layer and of the next two: the load sits two target layers ahead of its use (it was the
-  // single largest stall site of the first version: 24 % of all stall samples on `qsum * rdpk`)
-  T rdpk = R2[0], rdp_n1 = R2[plane], rdp_n2 = R2[2 * plane];
+  // 1/dp2 of the target layers reaches the thread through a four-deep cp.async ring (slot = k mod 4, stride `rstride`
+  // elements between slots): requested three target layers ahead, completed with cp.async.wait_group.  As a plain load it
+  // was the largest stall site (24 % of all stall samples on `qsum * rdpk`); rotated through registers two layers ahead it
+  // still cost 14 % because the compiler copies the freshly loaded register at the loop join and that copy waits at once.
+  auto r2_request = [&](int kk) {  // target layer kk (1-based), clamped
+    const int kc = kk <= km ? kk : km;
+    async_copy<sizeof(T)>(ring + (kk & 3) * rstride, R2 + (long)(kc - 1) * plane);
+    async_commit();
+  };
+  r2_request(1);
+  r2_request(2);
+  r2_request(3);
+  async_wait_pending<2>();
+  T rdpk = ring[(1 & 3) * rstride];
   bool started = false;
 
   auto finalize = [&](int kk, T x, T dpkk) {
@@ -266,9 +277,9 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
       dpk_m2 = dpk_m1;
       dpk_m1 = dpk;
       dpk = pe2k1 - pe2k;
-      rdpk = rdp_n1;
-      rdp_n1 = rdp_n2;
-      rdp_n2 = R2[(long)(k + 1 <= km - 1 ? k + 1 : km - 1) * plane];
+      r2_request(k + 2);
+      async_wait_pending<2>();  // at most the requests for k+1, k+2 are still in flight: 1/dp2(k) has landed
+      rdpk = ring[(k & 3) * rstride];
     }
   };
 
@@ -396,6 +407,7 @@ template <class T> __global__ void __launch_bounds__(128) k_remap_coef3(const Re
 template <class T, int AK, bool MAPN, int KM, int MINB> __global__ void __launch_bounds__(128, MINB) k_remap3(const Remap3Params<T> p) {
   // ak, bk in shared memory: pe2(k) = ak + bk*ps sits on the dependent path of the target-layer loop
   __shared__ T s_ak[KM + 1], s_bk[KM + 1];
+  __shared__ __align__(16) T s_ring[4 * 128];
   for (int k = threadIdx.x; k <= p.km; k += blockDim.x) {
     s_ak[k] = p.ak[k];
     s_bk[k] = p.bk[k];
@@ -406,7 +418,7 @@ template <class T, int AK, bool MAPN, int KM, int MINB> __global__ void __launch
   // through L2 (with the tracer as the slowest index every tracer streamed them from HBM again: 64 of 121 B per update)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  remap3_column<T, AK, MAPN, KM>(p, s_ak, s_bk, blockIdx.z, c % p.n + 1, c / p.n + 1, blockIdx.x);
+  remap3_column<T, AK, MAPN, KM>(p, s_ak, s_bk, s_ring + threadIdx.x, 128, blockIdx.z, c % p.n + 1, c / p.n + 1, blockIdx.x);
 }
 #endif
 

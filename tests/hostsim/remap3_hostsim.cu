@@ -11,7 +11,10 @@ static void run_cols(const Remap3Params<T>& p) {
   for (int t = 0; t < p.ntiles; ++t)
     for (int j = 1; j <= p.n; ++j)
       for (int i = 1; i <= p.n; ++i)
-        for (int iq = 0; iq < p.nq; ++iq) remap3_column<T, AK, true, 128>(p, p.ak, p.bk, t, i, j, iq);
+        for (int iq = 0; iq < p.nq; ++iq) {
+          T ring[4];
+          remap3_column<T, AK, true, 128>(p, p.ak, p.bk, ring, 1, t, i, j, iq);
+        }
 }
 
 template <class T>
