@@ -209,6 +209,7 @@ def main():
     updates_rank = 6 * n * n * npz * nq
 
     def step():
+        ctx.remap_prepare()   # pe of this step is resident and final (as after dyn_core): coefficients overlap the advection
         nsplt = ctx.tracer_2d_resident(nq, args.hord)
         ctx.remap_tracers_resident(nq, kord, fill=True)
         return nsplt
@@ -293,13 +294,13 @@ def main():
         h2d = sum(host[f].numel() * w for f in fields_in)
         d2h = (host["q"].numel() + host["delp"].numel()) * w
 
+        ak_h, bk_h, ptop_h = sd.hybrid(npz)
+
         def e2e_step():
-            for f in fields_in:
-                ctx.upload_ptr(f, host[f].data_ptr(), nq)
-            ctx.tracer_2d_resident(nq, args.hord)
-            ctx.remap_tracers_resident(nq, kord, fill=True)
-            ctx.download_ptr("q", host["q"].data_ptr(), nq)
-            ctx.download_ptr("delp", host["delp"].data_ptr(), nq)
+            # the public host-array call: tracer_2d + tracer remap, host buffers in and out (per-tracer copy/compute pipeline)
+            ctx.tracer_step(host["q"].data_ptr(), host["dp1"].data_ptr(), host["mfx"].data_ptr(), host["mfy"].data_ptr(),
+                            host["cx"].data_ptr(), host["cy"].data_ptr(), host["pe"].data_ptr(), ak_h, bk_h, ptop_h,
+                            host["delp"].data_ptr(), args.hord, kord, fill=True, nq=nq)
 
         e2e_step()  # warm-up
         barrier()

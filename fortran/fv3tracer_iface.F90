@@ -113,6 +113,90 @@ contains
 end module fv3tracer_iface_mod
 
 
+!> bind(C) interfaces of the device-resident / building-block entries (include/fv3tracer.h), 64-bit symbols shown; the
+!! 32-bit build binds the fv3t_f32_* names exactly as fv3tracer_iface_mod does.
+module fv3tracer_blocks_mod
+  use iso_c_binding
+  use fv3tracer_iface_mod, only: fv3t_real
+  implicit none
+  integer(c_int), parameter :: FV3T_Q = 0, FV3T_DP1 = 1, FV3T_MFX = 2, FV3T_MFY = 3, FV3T_CX = 4, FV3T_CY = 5, FV3T_PE = 6, &
+                               FV3T_DELP = 7
+  interface
+    integer(c_int) function fv3t_upload(ctx, field, host, nq) bind(C, name='fv3t_f64_upload')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field, nq
+      real(fv3t_real), intent(in) :: host(*)
+    end function
+    integer(c_int) function fv3t_download(ctx, field, host, nq) bind(C, name='fv3t_f64_download')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: field, nq
+      real(fv3t_real), intent(inout) :: host(*)
+    end function
+    integer(c_int) function fv3t_set_vertical(ctx, ak, bk, ptop) bind(C, name='fv3t_f64_set_vertical')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      real(fv3t_real), intent(in) :: ak(*), bk(*)
+      real(fv3t_real), value :: ptop
+    end function
+    integer(c_int) function fv3t_tracer_2d_begin(ctx, nq, q_split, cmax_local) bind(C, name='fv3t_f64_tracer_2d_begin')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nq, q_split
+      real(fv3t_real), intent(out) :: cmax_local(*)
+    end function
+    integer(c_int) function fv3t_tracer_2d_set_cmax(ctx, cmax_global, q_split, nsplt_out) bind(C, name='fv3t_f64_tracer_2d_set_cmax')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      real(fv3t_real), intent(in) :: cmax_global(*)
+      integer(c_int), value :: q_split
+      integer(c_int), intent(out) :: nsplt_out
+    end function
+    integer(c_int) function fv3t_halo_pack(ctx, it, local_tile, edge, dev_buf) bind(C, name='fv3t_f64_halo_pack')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, dev_buf
+      integer(c_int), value :: it, local_tile, edge
+    end function
+    integer(c_int) function fv3t_halo_unpack(ctx, it, local_tile, edge, dev_buf) bind(C, name='fv3t_f64_halo_unpack')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, dev_buf
+      integer(c_int), value :: it, local_tile, edge
+    end function
+    integer(c_int) function fv3t_tracer_2d_substep(ctx, it, hord, lim_fac) bind(C, name='fv3t_f64_tracer_2d_substep')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: it, hord
+      real(fv3t_real), value :: lim_fac
+    end function
+    integer(c_int) function fv3t_tracer_2d_finish(ctx) bind(C, name='fv3t_f64_tracer_2d_finish')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function fv3t_remap_prepare(ctx) bind(C, name='fv3t_f64_remap_prepare')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function fv3t_remap_tracers_resident(ctx, nq, kord_tr, fill) bind(C, name='fv3t_f64_remap_tracers_resident')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nq, fill
+      integer(c_int), intent(in) :: kord_tr(*)
+    end function
+    integer(c_int) function fv3t_neighbor(ctx, global_tile, edge, nbr_tile, nbr_edge, rotated) bind(C, name='fv3t_neighbor')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: global_tile, edge
+      integer(c_int), intent(out) :: nbr_tile, nbr_edge, rotated
+    end function
+    integer(c_size_t) function fv3t_halo_strip_elems(ctx) bind(C, name='fv3t_halo_strip_elems')
+      import :: c_ptr, c_size_t
+      type(c_ptr), value :: ctx
+    end function
+  end interface
+end module fv3tracer_blocks_mod
+
+
 !> Drop-in body for fv_tracer2d_mod::tracer_2d (same dummy list as model/fv_tracer2d.F90:324-345) for the usual
 !! decomposition of one MPI rank per tile (layout = 1,1); finer layouts need sub-tile contexts (SURVEY.md 8e, next round).
 !! The sub-step loop of the reference (:496-566) is kept on the host so that the q halo is exchanged where the reference

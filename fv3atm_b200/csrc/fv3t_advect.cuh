@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(512) k_cmax(const T* __restrict__ cx, const T*
 // (n+6)^2 planes, built from the 12-contact mosaic (fv_mp_mod.F90:581-629).
 template <class T>
 __global__ void k_halo_fill(T* __restrict__ q, const int* __restrict__ dst, const int* __restrict__ src, int len, int n, int npz,
-                            int nq, const int* __restrict__ ksplt, int it) {
+                            int nq, const int* __restrict__ ksplt, int it, int pl0 = 0) {
   const long plane = (long)(n + 6) * (n + 6);
   const long tile_stride = plane * npz * nq;
-  const int pl = blockIdx.y;  // iq*npz + kz
+  const int pl = pl0 + blockIdx.y;  // iq*npz + kz (pl0: first plane of a tracer sub-range)
   const int kz = pl % npz;
   if (it > ksplt[kz]) return;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < len; e += gridDim.x * blockDim.x) {

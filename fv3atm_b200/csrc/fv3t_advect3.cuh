@@ -69,6 +69,7 @@ template <class T> struct Adv3Params {
   const int* ksplt;
   int n, npz, nq, ntiles, it, W;
   T lim_fac;
+  int iq0 = 0, nql = -1;  // this launch advects tracers iq0 .. iq0+nql-1 of the nq resident ones (nql < 0: all)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -293,8 +294,8 @@ template <class T, int G> FV3T_HD bool adv3_make_cta(const Adv3Params<T>& p, int
   c.myoff = lev * n * (n + 1);
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const int iq = iqg * G + g;
-    c.live[g] = iq < p.nq;
+    const int iq = p.iq0 + iqg * G + g;
+    c.live[g] = iq < p.iq0 + (p.nql < 0 ? p.nq : p.nql);
     c.qoff[g] = (((long)t * p.nq + (c.live[g] ? iq : p.nq - 1)) * npz + kz) * (long)plane;
   }
   return true;

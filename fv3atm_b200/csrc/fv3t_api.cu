@@ -133,6 +133,11 @@ template <class T> struct Impl {
   T *rrx = nullptr, *rry = nullptr;
   fv3t::Pair<T>* P1 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
   T *GAM = nullptr, *RD1 = nullptr, *R2 = nullptr;
+  cudaStream_t side = nullptr;            // remap_prepare: the coefficient kernel runs here, concurrently with tracer_2d
+  cudaEvent_t ev_fork = nullptr, ev_coef = nullptr;
+  bool coef_ready = false, coef_wanted = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // tracer_step: copy streams of the per-tracer pipeline
+  std::vector<cudaEvent_t> ev_up, ev_done;
   bool fast = true;        // FV3T_STRICT=1 selects the bit-exact kernels for everything
   bool prep_done = true;   // steps A/C of the current tracer_2d call have been run (done lazily by the first sub-step)
   bool call_fast = false;  // the current tracer_2d call runs the fast kernels
@@ -220,6 +225,11 @@ template <class T> struct Impl {
   int finish();
   int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
   int remap_resident(int nq, const int* kord, int fill, int j_first, int j_count);
+  int remap_prepare();
+  int launch_coef_side();
+  int tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const T* hpe, const T* hak, const T* hbk, T hptop, T* hdelp, int nq,
+                  int hord, int q_split, T lim_fac, const int* kord, int fill, int* nsplt_out);
+  int remap_alloc();
 };
 
 template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g, int dev, void* strm) {
@@ -349,6 +359,13 @@ template <class T> int Impl<T>::destroy() {
   if (ev1) cudaEventDestroy(ev1);
   if (pe0) cudaEventDestroy(pe0);
   if (pe1) cudaEventDestroy(pe1);
+  if (side) cudaStreamDestroy(side);
+  if (s_h2d) cudaStreamDestroy(s_h2d);
+  if (s_d2h) cudaStreamDestroy(s_d2h);
+  for (cudaEvent_t e : ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_coef) cudaEventDestroy(ev_coef);
   if (own_stream) cudaStreamDestroy(stream);
   return 0;
 }
@@ -360,6 +377,7 @@ template <class T> int Impl<T>::upload(int f, const T* h, int nq) {
   CK(cudaSetDevice(device));
   CK(cudaMemcpyAsync(dptr, h, field_elems(f, nq) * sizeof(T), cudaMemcpyHostToDevice, stream));
   if (f == FV3T_Q) nq_cur = nq;
+  if (f == FV3T_PE) coef_ready = coef_wanted = false;
   return 0;
 }
 
@@ -562,6 +580,10 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     p.it = it;
     p.W = 0;
     p.lim_fac = lim_fac;
+    if (coef_wanted && it == 1 && !prof) {
+      const int rcs = launch_coef_side();
+      if (rcs) return rcs;
+    }
     kbegin();
     // 64-thread CTAs (58-column strips): measured fastest on B200 at C768 (131 ms vs 143 / 147 / 153 ms for 96 / 128 / 160
     // threads, profiles/r01_advect3_block_sweep.txt): three barriers per row step cost least when a CTA is two warps
@@ -695,6 +717,7 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
   if (!mapn)
     for (int iq = 0; iq < nq; ++iq) need_ppm |= kord[iq] <= 7;
   int rc = 0;
+  if (coef_ready) CK(cudaStreamWaitEvent(stream, ev_coef, 0));  // remap_prepare's side-stream kernel also writes delp
   bool fast_ok = fast && mapn && j_count == n && npz <= 128;
   const int ak0 = kord[0] < 0 ? -kord[0] : kord[0];
   for (int iq = 0; iq < nq; ++iq) {
@@ -702,16 +725,14 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
     fast_ok = fast_ok && fv3t::fast_kord_ok(a) && (a == ak0 || (a <= 8 && ak0 <= 8) || (a >= 17 && ak0 >= 17));
   }
   if (fast_ok) {
-    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
-    const size_t e1 = plane() * (npz + 1) * nt;
-    CK(dalloc((void**)&P1, e1 * sizeof(fv3t::Pair<T>)));
-    CK(dalloc((void**)&GAM, e1 * sizeof(T)));
-    CK(dalloc((void**)&RD1, sz_c() * nt * sizeof(T)));
-    CK(dalloc((void**)&R2, sz_c() * nt * sizeof(T)));
+    int rca = remap_alloc();
+    if (rca) return rca;
     fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, nq, nt, fill};
-    kbegin();
-    CK(fv3t::fast_remap_coef3<T>(p, stream));
-    kend(KC_SCALE);
+    if (!coef_ready) {  // otherwise computed ahead by remap_prepare on the side stream (waited for above)
+      kbegin();
+      CK(fv3t::fast_remap_coef3<T>(p, stream));
+      kend(KC_SCALE);
+    }
     kbegin();
     CK(fv3t::fast_remap3<T>(p, ak0, stream));
     kend(KC_REMAP);
@@ -768,9 +789,181 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
     else
       rc = mapn ? launch_remap2<T, 3, true>(*this, p) : launch_remap2<T, 3, false>(*this, p);
   }
+  coef_ready = coef_wanted = false;
   if (rc) return rc;
   if (j_count == n) cur ^= 1;
   nq_cur = nq;
+  return 0;
+}
+
+template <class T> int Impl<T>::remap_alloc() {
+  auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+  const size_t e1 = plane() * (npz + 1) * nt;
+  CK(dalloc((void**)&P1, e1 * sizeof(fv3t::Pair<T>)));
+  CK(dalloc((void**)&GAM, e1 * sizeof(T)));
+  CK(dalloc((void**)&RD1, sz_c() * nt * sizeof(T)));
+  CK(dalloc((void**)&R2, sz_c() * nt * sizeof(T)));
+  return 0;
+}
+
+// tracer_2d followed by the tracer remap for HOST arrays, as one call (the two are consecutive in fv_dynamics.F90:686-760).
+// Tracers never interact on this path, so after the tracer-independent fields are on the device the tracers are processed
+// one at a time in a three-stage pipeline -- upload of tracer iq+1 (copy stream 1) | halo + advection + remap of tracer iq
+// (context stream) | download of tracer iq-1 (copy stream 2) -- which keeps both PCIe directions busy at once and hides the
+// kernels behind the copies.  Post-state as fv3t_*_tracer_2d + fv3t_*_remap_tracers: q, delp always; dp1, cx, cy, mfx, mfy
+// only change when nsplt /= 1, and that (rare) case runs the unpipelined path.  Host arrays should be page-locked.
+template <class T>
+int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const T* hpe, const T* hak, const T* hbk, T hptop,
+                         T* hdelp, int nq, int hord, int q_split, T lim_fac, const int* kord, int fill, int* nsplt_out) {
+  if (nt != 6) return fail("fv3tracer: tracer_step needs all six tiles resident (ntiles = %d)", nt);
+  if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  CK(cudaSetDevice(device));
+  int rc;
+  CK(cudaMemcpyAsync(ak, hak, (npz + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(bk, hbk, (npz + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
+  ptop = hptop;
+  have_vertical = true;
+  coef_ready = coef_wanted = false;
+  if ((rc = upload(FV3T_DP1, hdp1, nq))) return rc;
+  if ((rc = upload(FV3T_MFX, hmfx, nq))) return rc;
+  if ((rc = upload(FV3T_MFY, hmfy, nq))) return rc;
+  if ((rc = upload(FV3T_CX, hcx, nq))) return rc;
+  if ((rc = upload(FV3T_CY, hcy, nq))) return rc;
+  if ((rc = upload(FV3T_PE, hpe, nq))) return rc;
+  std::vector<T> cm(npz);
+  if ((rc = begin(nq, q_split, cm.data()))) return rc;
+  if ((rc = set_cmax(cm.data(), q_split, nsplt_out))) return rc;
+  bool fast_remap = fast && nq > 5 && npz <= 128;
+  const int ak0 = kord[0] < 0 ? -kord[0] : kord[0];
+  for (int iq = 0; iq < nq; ++iq) {
+    const int a = kord[iq] < 0 ? -kord[iq] : kord[iq];
+    fast_remap = fast_remap && fv3t::fast_kord_ok(a) && (a == ak0 || (a <= 8 && ak0 <= 8) || (a >= 17 && ak0 >= 17));
+  }
+  if (nsplt != 1 || !fast || !fv3t::fast_hord_ok(hord) || !fast_remap || prof) {
+    // unpipelined: the sub-steps advance dp1 in place for all tracers at once, the strict kernels work on all tracers
+    if ((rc = upload(FV3T_Q, hq, nq))) return rc;
+    for (int it = 1; it <= nsplt; ++it) {
+      if ((rc = halo_local(it))) return rc;
+      if ((rc = substep(it, hord, lim_fac))) return rc;
+    }
+    if ((rc = finish())) return rc;
+    if ((rc = remap_resident(nq, kord, fill, 0, n))) return rc;
+    if ((rc = download(FV3T_Q, hq, nq))) return rc;
+    if ((rc = download(FV3T_DELP, hdelp, nq))) return rc;
+    if ((rc = download(FV3T_DP1, hdp1, nq))) return rc;
+    if (nsplt != 1) {
+      if ((rc = download(FV3T_MFX, hmfx, nq))) return rc;
+      if ((rc = download(FV3T_MFY, hmfy, nq))) return rc;
+      if ((rc = download(FV3T_CX, hcx, nq))) return rc;
+      if ((rc = download(FV3T_CY, hcy, nq))) return rc;
+    }
+    return 0;
+  }
+  // ---- pipelined path (nsplt == 1, fast kernels) ------------------------------------------------------------------------
+  if (!s_h2d) {
+    CK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+  }
+  while ((int)ev_up.size() < nq) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    ev_up.push_back(a);
+    ev_done.push_back(b);
+  }
+  nq_cur = nq;
+  if ((rc = prepare(hord))) return rc;  // k_prep3 (nsplt == 1: nothing is scaled in place)
+  if ((rc = remap_alloc())) return rc;
+  const int c0 = cur;                   // per tracer: advect q[c0] -> q[c0^1], remap q[c0^1] -> q[c0]
+  fv3t::Remap3Params<T> rp{q[c0 ^ 1], q[c0], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, nq, nt, fill};
+  CK(fv3t::fast_remap_coef3<T>(rp, stream));
+  ++launches;
+  const size_t chunk = plane() * npz;   // one (tile, tracer) block of q
+  const int forced = getenv("FV3T_ADV_NT") ? atoi(getenv("FV3T_ADV_NT")) : 0;
+  const int NT = (forced >= 32 && forced <= 256 && forced % 32 == 0) ? forced : 64;
+  for (int iq = 0; iq < nq; ++iq) {
+    for (int t = 0; t < nt; ++t) {
+      const size_t off = ((size_t)t * nq + iq) * chunk;
+      CK(cudaMemcpyAsync(q[c0] + off, hq + off, chunk * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+    }
+    CK(cudaEventRecord(ev_up[iq], s_h2d));
+    CK(cudaStreamWaitEvent(stream, ev_up[iq], 0));
+    if (halo_len) {
+      dim3 grid((halo_len + 255) / 256, npz);
+      fv3t::k_halo_fill<T><<<grid, 256, 0, stream>>>(q[c0], halo_dst, halo_src, halo_len, n, npz, nq, ksplt_d, 1, iq * npz);
+      ++launches;
+    }
+    fv3t::Adv3Params<T> p;
+    p.qin = q[c0];
+    p.qout = q[c0 ^ 1];
+    p.X2 = X2;
+    p.Y2 = Y2;
+    p.rrx = rrx;
+    p.rry = rry;
+    p.cab = cab;
+    p.mfx = mfx;
+    p.mfy = mfy;
+    p.area = area;
+    p.dxa = dxa;
+    p.dya = dya;
+    p.ksplt = ksplt_d;
+    p.n = n;
+    p.npz = npz;
+    p.nq = nq;
+    p.ntiles = nt;
+    p.it = 1;
+    p.W = 0;
+    p.lim_fac = lim_fac;
+    p.iq0 = iq;
+    p.nql = 1;
+    CK(fv3t::fast_advect3<T>(p, hord, NT, stream));
+    rp.iq0 = iq;
+    rp.nql = 1;
+    CK(fv3t::fast_remap3<T>(rp, ak0, stream));
+    launches += 2;
+    CK(cudaEventRecord(ev_done[iq], stream));
+    CK(cudaStreamWaitEvent(s_d2h, ev_done[iq], 0));
+    for (int t = 0; t < nt; ++t) {
+      const size_t off = ((size_t)t * nq + iq) * chunk;
+      CK(cudaMemcpyAsync(hq + off, q[c0] + off, chunk * sizeof(T), cudaMemcpyDeviceToHost, s_d2h));
+    }
+    if (iq == 0) CK(cudaMemcpyAsync(hdelp, delp, sz_c() * nt * sizeof(T), cudaMemcpyDeviceToHost, s_d2h));  // written by k_remap_coef3
+  }
+  CK(cudaStreamSynchronize(s_d2h));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  return 0;  // cur is unchanged: every tracer went q[c0] -> q[c0^1] -> q[c0]
+}
+
+// The Lagrangian pe is final when dyn_core returns, i.e. BEFORE tracer_2d is called (fv_dynamics.F90:600-704): the
+// tracer-independent remap coefficients (and delp <- dp2) can therefore be computed on a side stream while the advection
+// runs.  Valid until pe, ak, bk or ptop change; the next remap_tracers_resident consumes the result.
+template <class T> int Impl<T>::remap_prepare() {
+  if (!have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
+  if (!fast || npz > 128) return 0;  // strict kernels compute everything themselves
+  coef_wanted = true;                // launched by the next tracer_2d sub-step, right behind its bandwidth-bound preparation
+  return 0;
+}
+
+// k_remap_coef3 on the side stream, ordered after everything enqueued so far on the context's stream.  Called between the
+// (HBM-bound) preparation kernels of tracer_2d and its (issue-bound) advection kernel, so that the HBM-bound coefficient
+// kernel overlaps the advection instead of competing with k_cmax / k_prep3 for bandwidth.
+template <class T> int Impl<T>::launch_coef_side() {
+  coef_wanted = false;
+  if (!side) {
+    CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_coef, cudaEventDisableTiming));
+  }
+  int rc = remap_alloc();
+  if (rc) return rc;
+  fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, 0, nt, 1};
+  CK(cudaEventRecord(ev_fork, stream));
+  CK(cudaStreamWaitEvent(side, ev_fork, 0));
+  CK(fv3t::fast_remap_coef3<T>(p, side));
+  ++launches;
+  CK(cudaEventRecord(ev_coef, side));
+  coef_ready = true;
   return 0;
 }
 
@@ -827,6 +1020,7 @@ extern "C" int fv3t_device_count(void) {
     CK(cudaMemcpyAsync(I->bk, bk, (I->npz + 1) * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                            \
     CK(cudaStreamSynchronize(I->stream));                                                                                      \
     I->ptop = ptop;                                                                                                            \
+    I->coef_ready = I->coef_wanted = false;                                                                                    \
     I->have_vertical = true;                                                                                                   \
     return 0;                                                                                                                  \
   }                                                                                                                            \
@@ -837,6 +1031,17 @@ extern "C" int fv3t_device_count(void) {
   extern "C" int fv3t_##P##_remap_tracers_resident(fv3t_ctx* ctx, int nq, const int* kord_tr, int fill) {                      \
     NEED(ctx, P);                                                                                                              \
     return I->remap_resident(nq, kord_tr, fill, 0, I->n);                                                                      \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_step(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy,              \
+                                        const REAL* pe, const REAL* ak, const REAL* bk, REAL ptop, REAL* delp, int nq, int hord,  \
+                                        int q_split, REAL lim_fac, const int* kord_tr, int fill, int* nsplt_out) {               \
+    NEED(ctx, P);                                                                                                              \
+    if (!q || !dp1 || !mfx || !mfy || !cx || !cy || !pe || !ak || !bk || !delp || !kord_tr) return fail("fv3tracer: null argument"); \
+    return I->tracer_step(q, dp1, mfx, mfy, cx, cy, pe, ak, bk, ptop, delp, nq, hord, q_split, lim_fac, kord_tr, fill, nsplt_out); \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_remap_prepare(fv3t_ctx* ctx) {                                                                    \
+    NEED(ctx, P);                                                                                                              \
+    return I->remap_prepare();                                                                                                 \
   }                                                                                                                            \
   extern "C" int fv3t_##P##_tracer_2d(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,     \
                                       int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out,            \

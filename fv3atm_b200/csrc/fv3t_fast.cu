@@ -41,21 +41,22 @@ template <class T, int OI, int OO, int NTC, int MINB> static cudaError_t launch4
 template <class T, int OI, int OO> static cudaError_t launch3(Adv3Params<T>& p, int NT, cudaStream_t stream) {
   p.W = NT - 6;
   const int strips = (p.n + p.W - 1) / p.W;
+  const int nql = p.nql < 0 ? p.nq - p.iq0 : p.nql;
   // FV3T_ADV_RING=0 selects the register-prefetch kernel (k_advect3); default: the asynchronous-copy ring (k_advect4)
   static const int ring = getenv("FV3T_ADV_RING") ? atoi(getenv("FV3T_ADV_RING")) : 1;
   // tracers per thread of k_advect3 (tuning knob).  B200, C768: G = 1 131 ms, G = 2 177 ms, G = 3 211 ms (255 registers -> 8 warps/SM):
   // sharing the level fields does not pay for the lost occupancy (profiles/r01_advect3_block_sweep.txt)
   static const int grp = getenv("FV3T_ADV_G") ? atoi(getenv("FV3T_ADV_G")) : 1;
   if (ring) {
-    dim3 grid(p.nq, strips, p.ntiles * p.npz);
+    dim3 grid(nql, strips, p.ntiles * p.npz);
     if (NT <= 64) return launch4<T, OI, OO, 64, 8>(p, NT, grid, stream);
     return launch4<T, OI, OO, 256, 2>(p, NT, grid, stream);
   }
   if (grp == 2) {
-    dim3 grid((p.nq + 1) / 2, strips, p.ntiles * p.npz);
+    dim3 grid((nql + 1) / 2, strips, p.ntiles * p.npz);
     k_advect3<T, OI, OO, 2, 1><<<grid, NT, 0, stream>>>(p);
   } else {
-    dim3 grid(p.nq, strips, p.ntiles * p.npz);
+    dim3 grid(nql, strips, p.ntiles * p.npz);
     k_advect3<T, OI, OO, 1, 2><<<grid, NT, 0, stream>>>(p);
   }
   return cudaGetLastError();
@@ -81,7 +82,7 @@ template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaSt
 }
 
 template <class T, int AK> static cudaError_t launch_remap3(const Remap3Params<T>& p, cudaStream_t stream) {
-  dim3 grid(p.nq, (p.n * p.n + 127) / 128, p.ntiles);
+  dim3 grid(p.nql < 0 ? p.nq - p.iq0 : p.nql, (p.n * p.n + 127) / 128, p.ntiles);
   static const int minb = getenv("FV3T_REMAP_MINB") ? atoi(getenv("FV3T_REMAP_MINB")) : 4;  // tuning knob: 4 -> 128 regs, 5 -> 96, 6 -> 80
   if (minb == 5)
     k_remap3<T, AK, true, 128, 5><<<grid, 128, 0, stream>>>(p);

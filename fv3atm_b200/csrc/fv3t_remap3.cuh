@@ -32,6 +32,7 @@ template <class T> struct Remap3Params {
   T* R2;           // (isd:ied, jsd:jed, km): 1/dp2
   T ptop;
   int n, km, nq, ntiles, fill;
+  int iq0 = 0, nql = -1;  // this launch remaps tracers iq0 .. iq0+nql-1 of the nq resident ones (nql < 0: all)
 };
 
 // ---- tracer-independent column coefficients ---------------------------------------------------------------------------
@@ -418,7 +419,7 @@ template <class T, int AK, bool MAPN, int KM, int MINB> __global__ void __launch
   // through L2 (with the tracer as the slowest index every tracer streamed them from HBM again: 64 of 121 B per update)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  remap3_column<T, AK, MAPN, KM>(p, s_ak, s_bk, s_ring + threadIdx.x, 128, blockIdx.z, c % p.n + 1, c / p.n + 1, blockIdx.x);
+  remap3_column<T, AK, MAPN, KM>(p, s_ak, s_bk, s_ring + threadIdx.x, 128, blockIdx.z, c % p.n + 1, c / p.n + 1, p.iq0 + blockIdx.x);
 }
 #endif
 

@@ -17,6 +17,11 @@ from .devarray import field_view
 NG = cs.NG
 
 
+def hybrid(npz: int):
+    """(ak, bk, ptop) of the synthetic hybrid coordinate fill_context uses."""
+    return sy.hybrid_coordinate(npz)
+
+
 def fill_context(ctx, grid: cs.Grid, nq: int, courant: float = 0.7, divergent: float = 0.15, seed: int = 20260101,
                  lagrangian_perturb: float = 0.3, device: int = 0, q_first: int = 0):
     """Fill q, dp1, cx, cy, mfx, mfy, pe of `ctx` (its resident tiles; tracers q_first .. q_first+nq-1 of the global

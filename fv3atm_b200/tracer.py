@@ -75,6 +75,20 @@ class TracerContext:
         L.check(self._f("remap_tracers")(self._h, L.ptr(pe), L.ptr(ak), L.ptr(bk), self._ct(ptop), L.ptr(q), L.ptr(delp),
                                          int(nq), L.ptr(kord), int(bool(fill))))
 
+    def tracer_step(self, q, dp1, mfx, mfy, cx, cy, pe, ak, bk, ptop, delp, hord, kord_tr, q_split=0, lim_fac=1.0, fill=True, nq=None):
+        """tracer_2d + tracer remap on host arrays as one call, pipelined per tracer (fv3t_*_tracer_step).  Arguments are numpy
+        arrays or integer addresses of (page-locked) host buffers; in place like the two separate calls.  Returns nsplt."""
+        nq = int(nq) if nq is not None else (q.shape[1] if hasattr(q, "shape") else int(self.nq_max))
+        kord = np.ascontiguousarray(np.broadcast_to(np.asarray(kord_tr, dtype=np.int32), (nq,)))
+        ak = np.ascontiguousarray(ak, dtype=self.dtype)
+        bk = np.ascontiguousarray(bk, dtype=self.dtype)
+        P = lambda a: C.c_void_p(a) if isinstance(a, int) else L.ptr(a)
+        nsplt = C.c_int(0)
+        L.check(self._f("tracer_step")(self._h, P(q), P(dp1), P(mfx), P(mfy), P(cx), P(cy), P(pe), L.ptr(ak), L.ptr(bk),
+                                       self._ct(ptop), P(delp), int(nq), int(hord), int(q_split), self._ct(lim_fac), L.ptr(kord),
+                                       int(bool(fill)), C.byref(nsplt)))
+        return nsplt.value
+
     def mapn_tracer(self, nq, km, pe1, pe2, q1, dp2, kord, j, i1, i2, isd, ied, jsd, jed, q_min, fill):
         """Row-granular entry with the reference's own argument list (one-tile context)."""
         kord = np.ascontiguousarray(kord, dtype=np.int32)
@@ -109,6 +123,10 @@ class TracerContext:
         nsplt = C.c_int(0)
         L.check(self._f("tracer_2d_resident")(self._h, int(nq), int(hord), int(q_split), self._ct(lim_fac), C.byref(nsplt)))
         return nsplt.value
+
+    def remap_prepare(self):
+        """Hint: the resident pe is final for this step -> remap coefficients are computed concurrently with tracer_2d."""
+        L.check(self._f("remap_prepare")(self._h))
 
     def remap_tracers_resident(self, nq, kord_tr, fill=True):
         kord = np.ascontiguousarray(np.broadcast_to(np.asarray(kord_tr, dtype=np.int32), (nq,)))

@@ -98,12 +98,26 @@ int fv3t_device_count(void);
                              const int* kord, int j, int i1, int i2, int isd, int ied, int jsd, int jed, REAL q_min,   \
                              int fill);                                                                                 \
                                                                                                                         \
+  /* tracer_2d immediately followed by the tracer remap (they are consecutive in ACS/model/fv_dynamics.F90:686-760), host    \
+     arrays in and out, as ONE call: same arguments, same post-state as fv3t_*_tracer_2d + fv3t_*_remap_tracers (q, delp;     \
+     dp1, cx, cy, mfx, mfy when nsplt /= 1).  Tracers are independent on this path, so they are pipelined one by one:         \
+     upload of tracer i+1 | kernels of tracer i | download of tracer i-1, both PCIe directions busy at once.  Host arrays      \
+     should be page-locked.  Needs ntiles == 6. */                                                                           \
+  int fv3t_##P##_tracer_step(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, const REAL* pe,   \
+                             const REAL* ak, const REAL* bk, REAL ptop, REAL* delp, int nq, int hord, int q_split,          \
+                             REAL lim_fac, const int* kord_tr, int fill, int* nsplt_out);                                    \
+                                                                                                                        \
   /* Device-resident operation (north star: tracers, Courant numbers, mass fluxes and delp stay in HBM). */            \
   int fv3t_##P##_upload(fv3t_ctx* ctx, int field, const REAL* host, int nq);                                            \
   int fv3t_##P##_download(fv3t_ctx* ctx, int field, REAL* host, int nq);                                                \
   int fv3t_##P##_set_vertical(fv3t_ctx* ctx, const REAL* ak, const REAL* bk, REAL ptop);                                \
   int fv3t_##P##_tracer_2d_resident(fv3t_ctx* ctx, int nq, int hord, int q_split, REAL lim_fac, int* nsplt_out);        \
   int fv3t_##P##_remap_tracers_resident(fv3t_ctx* ctx, int nq, const int* kord_tr, int fill);                           \
+  /* Optional hint: the resident pe is final for this step (it is when dyn_core returns, before tracer_2d is called,    \
+     ACS/model/fv_dynamics.F90:600-704), so the tracer-independent remap coefficients and delp may be computed on a     \
+     side stream while tracer_2d runs.  Consumed by the next remap_tracers_resident; invalidated by uploading pe or      \
+     set_vertical.  Do not write pe through fv3t_device_ptr between this call and the remap. */                          \
+  int fv3t_##P##_remap_prepare(fv3t_ctx* ctx);                                                                           \
                                                                                                                         \
   /* Building blocks for a context that holds only some tiles (face sharding): the caller transports the packed       \
      edge strips between contexts (NCCL send/recv in this repo, MPI in a Fortran host) and reduces cmax.               \

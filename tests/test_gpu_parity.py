@@ -315,3 +315,63 @@ def test_row_granular_mapn_tracer_entry(oracle, case_factory, mode):
     ctx.close()
     sl = slice(NG, -NG)
     assert np.array_equal(q1[..., sl, sl], qref[0][..., sl, sl])
+
+
+def test_remap_prepare_overlap_is_transparent(oracle, case_factory, mode):
+    """fv3t_*_remap_prepare (coefficients + delp on a side stream while tracer_2d runs) must not change any result, and a pe
+    upload after it must invalidate it."""
+    case = case_factory(24, 16, 9, "float64", courant=0.7)
+    kord = np.full(9, 9, dtype=np.int32)
+    outs = []
+    for prepare in (False, True, "stale"):
+        ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+        for f in ("q", "dp1", "mfx", "mfy", "cx", "cy"):
+            ctx.upload(f, getattr(case, f), case.nq)
+        ctx.set_vertical(case.ak, case.bk, case.ptop)
+        if prepare == "stale":
+            ctx.upload("pe", np.ascontiguousarray(case.pe[::-1]), case.nq)   # wrong pe ...
+            ctx.remap_prepare()
+        ctx.upload("pe", case.pe, case.nq)                                    # ... replaced: the prepared coefficients are dropped
+        if prepare is True:
+            ctx.remap_prepare()
+        ctx.tracer_2d_resident(case.nq, 8)
+        ctx.remap_tracers_resident(case.nq, kord, fill=True)
+        q = np.empty_like(case.q)
+        delp = np.empty_like(case.dp1)
+        ctx.download("q", q, case.nq)
+        ctx.download("delp", delp, case.nq)
+        ctx.close()
+        outs.append((q, delp))
+    sl = slice(NG, -NG)
+    for q, delp in outs[1:]:
+        assert np.array_equal(q[..., sl, sl], outs[0][0][..., sl, sl])
+        assert np.array_equal(delp[..., sl, sl], outs[0][1][..., sl, sl])
+
+
+@pytest.mark.parametrize("courant", [0.7, 1.8])
+def test_tracer_step_equals_the_two_separate_calls(oracle, case_factory, courant, mode):
+    """fv3t_*_tracer_step (tracer_2d + remap on host arrays, pipelined per tracer when nsplt == 1) leaves exactly the
+    post-state of fv3t_*_tracer_2d followed by fv3t_*_remap_tracers."""
+    case = case_factory(24, 16, 9, "float64", courant=courant)
+    kord = np.full(9, 9, dtype=np.int32)
+    a = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+    nsplt_a, _ = ctx.tracer_2d(a["q"], a["dp1"], a["mfx"], a["mfy"], a["cx"], a["cy"], 8)
+    delp_a = np.zeros_like(case.dp1)
+    ctx.remap_tracers(case.pe, case.ak, case.bk, case.ptop, a["q"], delp_a, kord, fill=True)
+    ctx.close()
+    b = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    delp_b = np.zeros_like(case.dp1)
+    ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+    nsplt_b = ctx.tracer_step(b["q"], b["dp1"], b["mfx"], b["mfy"], b["cx"], b["cy"], case.pe, case.ak, case.bk, case.ptop, delp_b,
+                              8, kord, fill=True)
+    launches = ctx.kernel_launches()
+    ctx.close()
+    assert nsplt_a == nsplt_b and (nsplt_b == 1) == (courant < 1)
+    sl = slice(NG, -NG)
+    assert np.array_equal(a["q"][..., sl, sl], b["q"][..., sl, sl])
+    assert np.array_equal(delp_a[..., sl, sl], delp_b[..., sl, sl])
+    assert np.array_equal(a["dp1"][..., sl, sl], b["dp1"][..., sl, sl])
+    for k in ("cx", "cy", "mfx", "mfy"):
+        assert np.array_equal(a[k], b[k]), k
+    assert launches > 0

@@ -81,6 +81,15 @@ def test_discontinuous_schemes_stay_on_the_strict_path(sim, oracle, case_factory
     assert nd[2] > 1e-9, nd
 
 
+def test_async_ring_variant_fp32(sim, oracle, case_factory):
+    case = case_factory(12, 8, 9, "float32", courant=1.8)
+    ref = oracle.tracer_2d(case, hord=8)
+    ring = run_sim(sim, case, 8, ref, NT=32, group=4)
+    regs = run_sim(sim, case, 8, ref, NT=32, group=1)
+    assert np.array_equal(ring["q"], regs["q"])
+    assert norm_diff(ring["q"], ref["q"]).max() <= 1e-5
+
+
 @pytest.mark.parametrize("hord", [8, 10, 13])
 @pytest.mark.parametrize("courant", [0.7, 1.8])
 def test_async_ring_variant_equals_register_prefetch_variant(sim, oracle, case_factory, hord, courant):
