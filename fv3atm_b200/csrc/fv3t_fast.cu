@@ -26,13 +26,9 @@ template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cud
 
 template <class T, int OI, int OO, int NTC, int MINB> static cudaError_t launch4(const Adv3Params<T>& p, int NT, dim3 grid, cudaStream_t stream) {
   constexpr size_t smem = (size_t)Adv4Layout<NTC>::TOTAL * sizeof(T);
-  if (smem > 48 * 1024) {
-    static bool once = false;
-    if (!once) {
-      cudaError_t e = cudaFuncSetAttribute(k_advect4<T, OI, OO, NTC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      once = true;
-    }
+  if (smem > 48 * 1024) {  // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+    cudaError_t e = cudaFuncSetAttribute(k_advect4<T, OI, OO, NTC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
   }
   k_advect4<T, OI, OO, NTC, MINB><<<grid, NT, smem, stream>>>(p);
   return cudaGetLastError();
