@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/b.json 2> gpurun_out/b.err; python -c "import json,sys; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['roofline']['kernels'])"; tail -2 gpurun_out/b.err
-timeout 600 python -m pytest tests -m gpu -q -k "tracer_2d or config1 or extremes or tracer_step" 2>&1 | tail -2
+( timeout 600 python bench.py --n 384 --dtype float32 --steps 5 --warmup 3 --no-cpu ) > gpurun_out/bench_c384_f32.json 2> gpurun_out/bench_c384_f32.err; tail -c 300 gpurun_out/bench_c384_f32.json; echo
+( timeout 600 python bench.py --n 384 --nq 30 --steps 3 --warmup 3 --no-cpu --no-e2e ) > gpurun_out/bench_c384_nq30.json 2> gpurun_out/bench_c384_nq30.err; tail -c 300 gpurun_out/bench_c384_nq30.json; echo
+( timeout 600 python bench.py --n 384 --dtype float32 --hord 13 --steps 3 --warmup 3 --no-cpu --no-e2e ) > gpurun_out/bench_c384_f32_h13.json 2> gpurun_out/bench_c384_f32_h13.err; tail -c 200 gpurun_out/bench_c384_f32_h13.json; echo
