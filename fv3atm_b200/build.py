@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libfv3tracer.so")
 # Two translation units: the strict kernels + host orchestration keep the bit-exact contract with the FMA-free oracle
 # (no contraction, IEEE division/sqrt); the production kernels (fv3t_fast.cu) are built with FMA contraction on.
 SOURCES = {"fv3t_api.cu": ["--fmad=false"], "fv3t_fast.cu": ["--fmad=true"]}
-HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_remap.cuh",
+HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_remap.cuh",
            "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
 
 NVCC_FLAGS = [

@@ -1,5 +1,6 @@
 // fv3atm_b200: support kernels of the horizontal tracer advection (tracer_2d) for sm_100a: per-level Courant maxima,
-// intra-GPU edge-halo fill, level gather.  The transport kernel itself is fv3t_advect2.cuh.
+// intra-GPU edge-halo fill, level gather.  The transport kernels are fv3t_advect2.cuh (strict), fv3t_advect3.cuh /
+// fv3t_advect4.cuh (fast: register prefetch / cp.async input ring).
 //
 // Data layout in HBM = the Fortran layout of the host arrays, tile-major:
 //   q   (isd:ied, jsd:jed, npz, nq)  two buffers (ping-pong: a sub-step reads one and writes the other,
