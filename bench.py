@@ -43,14 +43,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=768, help="cells per tile edge (C768)")
+    ap.add_argument("--n", "--ncell", dest="n", type=int, default=768,
+                    help="cells per tile edge (C768); use --ncell under torchrun, whose own parser claims the prefix --n")
     ap.add_argument("--npz", type=int, default=127)
     ap.add_argument("--nq", type=int, default=9)
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--hord", type=int, default=8)
     ap.add_argument("--kord", type=int, default=9)
     ap.add_argument("--courant", type=float, default=0.7)
-    ap.add_argument("--shard", default="tracer", choices=["tracer", "face"])
+    ap.add_argument("--shard", default="tracer", choices=["tracer", "face", "group"],
+                    help="tracer: every rank its own nq tracers (weak); face / group: ONE nq-tracer problem split by faces x tracer groups / by tracer groups only (strong)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -196,9 +198,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    if args.shard == "face" and world > 1:
+    if args.shard in ("face", "group") and world > 1:
         from fv3atm_b200 import partition
-        return partition.bench_face_sharded(args, rank, world, local_rank)
+        return partition.bench_face_sharded(args, rank, world, local_rank, prefer="face" if args.shard == "face" else "tracer")
 
     n, npz, nq = args.n, args.npz, args.nq
     grid = cs.make_grid(n)

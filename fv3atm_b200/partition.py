@@ -240,7 +240,7 @@ class ShardedTracerStep:
         self.ctx.remap_tracers_resident(self.nq_local, kord, fill)
 
 
-def bench_face_sharded(args, rank: int, world: int, local_rank: int) -> int:
+def bench_face_sharded(args, rank: int, world: int, local_rank: int, prefer: str = "face") -> int:
     """bench.py --shard face: ONE global problem (6 faces x nq tracers) split over the ranks as F face groups x G tracer
     groups (strong scaling).  Per sub-step one grouped NCCL send/recv of the packed edge strips between face groups and,
     per call, one all-reduce(MAX) of cmax; everything (kernels, pack/unpack, NCCL) is ordered on one CUDA stream."""
@@ -251,7 +251,7 @@ def bench_face_sharded(args, rank: int, world: int, local_rank: int) -> int:
     from .tracer import TracerContext
 
     n, npz, nq = args.n, args.npz, args.nq
-    F, G = choose_layout(world, nq, prefer="face")
+    F, G = choose_layout(world, nq, prefer=prefer)
     layout = Layout(world, F, G, nq)
     tiles = layout.tiles(rank)
     q_first, nq_local = layout.tracers(rank)
@@ -298,7 +298,8 @@ def bench_face_sharded(args, rank: int, world: int, local_rank: int) -> int:
                 "config": {"workload": f"C{n} L{npz}, {nq} tracers in total, {args.dtype}, hord_tr={args.hord}, kord_tr={args.kord}, fill, "
                                        f"tracer_2d + tracer remap",
                            "parallelism": f"{F} face groups x {G} tracer groups; rank 0: tiles {list(tiles)}, {nq_local} tracers",
-                           "halo": f"{len(sends)} NCCL send/recv strips of {strip_bytes} B per rank and sub-step + all-reduce(max) of cmax",
+                           "halo": (f"{len(sends)} NCCL send/recv strips of {strip_bytes} B per rank and sub-step + all-reduce(max) of cmax"
+                                    if F > 1 else "none: tracer groups only, winds / mass fluxes / delp replicated (no data-path collective)"),
                            "nsplt": int(nsplt), "updates_per_step": updates,
                            "l2": "inputs (GBs per rank) far exceed the 126 MB L2; no flush needed"},
                 "gpu_launches": int(launches), "e2e": None, "roofline": None, "cpu_baseline": None, "clocks": None}
