@@ -185,12 +185,14 @@ def main():
     from fv3atm_b200 import synthetic_device as sd
     from fv3atm_b200.build import build as build_lib
 
-    if rank == 0:
-        build_lib()
+    torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    torch.cuda.set_device(local_rank)
+    if rank == 0:
+        build_lib()   # no-op when the in-tree library is up to date
+    if world > 1:
+        dist.barrier()  # nobody loads the library before rank 0 has (re)built it
     dev = torch.device(f"cuda:{local_rank}")
 
     def barrier():
