@@ -88,7 +88,7 @@ def sim3():
     src = os.path.join(SIM, "remap3_hostsim.cu")
     csrc = os.path.join(HERE, "..", "fv3atm_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("fv3t_remap3.cuh", "fv3t_remap2.cuh", "fv3t_remap.cuh", "fv3t_common.cuh",
-                                                     "fv3t_advect3.cuh")]
+                                                     "fv3t_advect3.cuh", "fv3t_advect4.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["nvcc", "-x", "cu", "-O2", "-std=c++17", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC,-fno-fast-math", "-shared", "-o", so, src], check=True, cwd=SIM)
