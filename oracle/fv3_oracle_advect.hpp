@@ -774,4 +774,155 @@ static void tracer_2d_mosaic(const Mosaic<T>& m, int hord, int q_split, T lim_fa
   }
 }
 
+// -----------------------------------------------------------------------------------------------------
+// tracer_2d_1L (fv_tracer2d.F90:92-321): the level-at-a-time variant fv_dynamics calls when z_tracer is set
+// (fv_dynamics.F90:696-698).  Same arithmetic as tracer_2d but a different driver: the sub-step count is
+// per level (nsplt = int(1 + cmax(k)), :201-202, :254), the level's tracers are staged in qn2 (:263-270), q is
+// written only by the last sub-step (:282-288) and qn2's halo is refreshed with a blocking update between the
+// sub-steps of that level (:314).  q_split is not used by this routine.  Restated independently of
+// tracer_2d_mosaic so that the two can pin each other: for trdm2 = 0 every output must be
+// bit-identical.
+// -----------------------------------------------------------------------------------------------------
+template <class T>
+static void tracer_2d_1L_mosaic(const Mosaic<T>& m, int hord, T lim_fac, int* nsplt_max_out, int* ksplt_out, T* cmax_out) {
+  const Bounds bd = Bounds::tile(m.n);
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const int npx = bd.npx, npy = bd.npy, npz = m.npz, nq = m.nq;
+  const long nxd = ied - isd + 1, nyd = jed - jsd + 1, nx = ie - is + 1, ny = je - js + 1;
+  const long sz_q2 = nxd * nyd, sz_cx2 = (nx + 1) * nyd, sz_cy2 = nxd * (ny + 1), sz_mfx2 = (nx + 1) * ny,
+             sz_mfy2 = nx * (ny + 1);
+  std::vector<T> xfx_all((size_t)m.ntiles * sz_cx2 * npz), yfx_all((size_t)m.ntiles * sz_cy2 * npz);
+  std::vector<T> cmax(npz, T(0));
+
+  // xfx, yfx, cmax per level (:179-214), every tile playing one rank; mp_reduce_max (:225) = max over tiles
+  for (int k = 1; k <= npz; ++k) {
+    T cm_all = T(0);
+    for (int t = 0; t < m.ntiles; ++t) {
+      const GridT<T>& g = m.grid[t];
+      V2<const T> dxa{g.dxa, isd, jsd, nxd}, dya{g.dya, isd, jsd, nxd}, dx{g.dx, isd, jsd, nxd}, dy{g.dy, isd, jsd, nxd + 1};
+      auto sin_sg = [&](int i, int j, int p) -> T { return g.sin_sg[(long)(i - isd) + (long)(j - jsd) * nxd + (long)(p - 1) * sz_q2]; };
+      V2<const T> cx{m.cx + (size_t)t * sz_cx2 * npz + (size_t)(k - 1) * sz_cx2, is, jsd, nx + 1};
+      V2<const T> cy{m.cy + (size_t)t * sz_cy2 * npz + (size_t)(k - 1) * sz_cy2, isd, js, nxd};
+      V2<T> xfx{xfx_all.data() + (size_t)t * sz_cx2 * npz + (size_t)(k - 1) * sz_cx2, is, jsd, nx + 1};
+      V2<T> yfx{yfx_all.data() + (size_t)t * sz_cy2 * npz + (size_t)(k - 1) * sz_cy2, isd, js, nxd};
+      for (int j = jsd; j <= jed; ++j)
+        for (int i = is; i <= ie + 1; ++i)
+          xfx(i, j) = (cx(i, j) > T(0)) ? cx(i, j) * dxa(i - 1, j) * dy(i, j) * sin_sg(i - 1, j, 3)
+                                        : cx(i, j) * dxa(i, j) * dy(i, j) * sin_sg(i, j, 1);
+      for (int j = js; j <= je + 1; ++j)
+        for (int i = isd; i <= ied; ++i)
+          yfx(i, j) = (cy(i, j) > T(0)) ? cy(i, j) * dya(i, j - 1) * dx(i, j) * sin_sg(i, j - 1, 4)
+                                        : cy(i, j) * dya(i, j) * dx(i, j) * sin_sg(i, j, 2);
+      T cm = T(0);
+      if (k < npz / 6) {
+        for (int j = js; j <= je; ++j)
+          for (int i = is; i <= ie; ++i) cm = f_max(cm, f_abs(cx(i, j)), f_abs(cy(i, j)));
+      } else {
+        for (int j = js; j <= je; ++j)
+          for (int i = is; i <= ie; ++i) cm = f_max(cm, f_max(f_abs(cx(i, j)), f_abs(cy(i, j))) + T(1) - sin_sg(i, j, 5));
+      }
+      cm_all = (t == 0) ? cm : f_max(cm_all, cm);
+    }
+    cmax[k - 1] = cm_all;
+  }
+  // per-level sub-step count and in-place scaling (:227-259)
+  int nsplt_max = 1;
+  for (int k = 1; k <= npz; ++k) {
+    const int nsplt = (int)(T(1) + cmax[k - 1]);
+    if (ksplt_out) ksplt_out[k - 1] = nsplt;
+    nsplt_max = nsplt > nsplt_max ? nsplt : nsplt_max;
+    if (nsplt > 1) {
+      const T frac = T(1) / (T)nsplt;
+      for (int t = 0; t < m.ntiles; ++t) {
+        T* cx = m.cx + (size_t)t * sz_cx2 * npz + (size_t)(k - 1) * sz_cx2;
+        T* xf = xfx_all.data() + (size_t)t * sz_cx2 * npz + (size_t)(k - 1) * sz_cx2;
+        for (long e = 0; e < sz_cx2; ++e) {
+          cx[e] = cx[e] * frac;
+          xf[e] = xf[e] * frac;
+        }
+        T* mfx = m.mfx + (size_t)t * sz_mfx2 * npz + (size_t)(k - 1) * sz_mfx2;
+        for (long e = 0; e < sz_mfx2; ++e) mfx[e] = mfx[e] * frac;
+        T* cy = m.cy + (size_t)t * sz_cy2 * npz + (size_t)(k - 1) * sz_cy2;
+        T* yf = yfx_all.data() + (size_t)t * sz_cy2 * npz + (size_t)(k - 1) * sz_cy2;
+        for (long e = 0; e < sz_cy2; ++e) {
+          cy[e] = cy[e] * frac;
+          yf[e] = yf[e] * frac;
+        }
+        T* mfy = m.mfy + (size_t)t * sz_mfy2 * npz + (size_t)(k - 1) * sz_mfy2;
+        for (long e = 0; e < sz_mfy2; ++e) mfy[e] = mfy[e] * frac;
+      }
+    }
+  }
+  if (nsplt_max_out) *nsplt_max_out = nsplt_max;
+  if (cmax_out) std::memcpy(cmax_out, cmax.data(), sizeof(T) * npz);
+
+  halo_update(m);  // complete_group_halo_update(q_pack) (:261)
+
+  // level loop (:268-319); qn2(isd:ied, jsd:jed, nq) per tile
+  std::vector<T> qn2((size_t)m.ntiles * sz_q2 * nq);
+  Tp2dScratch<T> w;
+  w.size(bd);
+  for (int k = 1; k <= npz; ++k) {
+    const int nsplt = (int)(T(1) + cmax[k - 1]);
+    for (int it = 1; it <= nsplt; ++it) {
+      for (int t = 0; t < m.ntiles; ++t) {
+        const GridT<T>& g = m.grid[t];
+        V2<const T> area{g.area, isd, jsd, nxd}, rarea{g.rarea, isd, jsd, nxd};
+        V2<T> dp1{m.dp1 + (size_t)t * sz_q2 * npz + (size_t)(k - 1) * sz_q2, isd, jsd, nxd};
+        V2<const T> mfx{m.mfx + (size_t)t * sz_mfx2 * npz + (size_t)(k - 1) * sz_mfx2, is, js, nx + 1};
+        V2<const T> mfy{m.mfy + (size_t)t * sz_mfy2 * npz + (size_t)(k - 1) * sz_mfy2, is, js, nx};
+        V2<const T> cx{m.cx + (size_t)t * sz_cx2 * npz + (size_t)(k - 1) * sz_cx2, is, jsd, nx + 1};
+        V2<const T> cy{m.cy + (size_t)t * sz_cy2 * npz + (size_t)(k - 1) * sz_cy2, isd, js, nxd};
+        V2<const T> xfx{xfx_all.data() + (size_t)t * sz_cx2 * npz + (size_t)(k - 1) * sz_cx2, is, jsd, nx + 1};
+        V2<const T> yfx{yfx_all.data() + (size_t)t * sz_cy2 * npz + (size_t)(k - 1) * sz_cy2, isd, js, nxd};
+        V2<T> dp2{w.dp2.data(), is, js, nx};
+        V2<T> ra_x{w.ra_x.data(), is, jsd, nx};
+        V2<T> ra_y{w.ra_y.data(), isd, js, nxd};
+        V2<T> fx{w.fx.data(), is, js, nx + 1};
+        V2<T> fy{w.fy.data(), is, js, nx};
+        for (int j = jsd; j <= jed; ++j) {  // :270-279 (hoisted out of the it loop in the reference; same values)
+          for (int i = is; i <= ie; ++i) ra_x(i, j) = area(i, j) + xfx(i, j) - xfx(i + 1, j);
+          if (j >= js && j <= je)
+            for (int i = isd; i <= ied; ++i) ra_y(i, j) = area(i, j) + yfx(i, j) - yfx(i, j + 1);
+        }
+        for (int j = js; j <= je; ++j)
+          for (int i = is; i <= ie; ++i)
+            dp2(i, j) = dp1(i, j) + (mfx(i, j) - mfx(i + 1, j) + mfy(i, j) - mfy(i, j + 1)) * rarea(i, j);
+        for (int iq = 1; iq <= nq; ++iq) {
+          V2<T> q{m.q + (size_t)t * sz_q2 * npz * nq + ((size_t)(iq - 1) * npz + (k - 1)) * sz_q2, isd, jsd, nxd};
+          V2<T> qn{qn2.data() + ((size_t)t * nq + (iq - 1)) * sz_q2, isd, jsd, nxd};
+          if (nsplt != 1) {
+            if (it == 1)
+              for (int j = jsd; j <= jed; ++j)
+                for (int i = isd; i <= ied; ++i) qn(i, j) = q(i, j);
+            fv_tp_2d<T>(qn, cx, cy, npx, npy, hord, fx, fy, xfx, yfx, g, bd, V2<const T>{ra_x.p, is, jsd, nx},
+                        V2<const T>{ra_y.p, isd, js, nxd}, lim_fac, mfx.p, mfy.p, w);
+            V2<T> dst = (it < nsplt) ? qn : q;
+            for (int j = js; j <= je; ++j)
+              for (int i = is; i <= ie; ++i)
+                dst(i, j) = (qn(i, j) * dp1(i, j) + (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1)) * rarea(i, j)) / dp2(i, j);
+          } else {
+            fv_tp_2d<T>(q, cx, cy, npx, npy, hord, fx, fy, xfx, yfx, g, bd, V2<const T>{ra_x.p, is, jsd, nx},
+                        V2<const T>{ra_y.p, isd, js, nxd}, lim_fac, mfx.p, mfy.p, w);
+            for (int j = js; j <= je; ++j)
+              for (int i = is; i <= ie; ++i)
+                q(i, j) = (q(i, j) * dp1(i, j) + (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1)) * rarea(i, j)) / dp2(i, j);
+          }
+        }
+        if (it < nsplt)
+          for (int j = js; j <= je; ++j)
+            for (int i = is; i <= ie; ++i) dp1(i, j) = dp2(i, j);
+      }
+      if (it < nsplt) {  // mpp_update_domains(qn2, domain) (:314): edge halos of every tracer slab of this level
+        const int64_t plane = sz_q2, tile_stride = plane * nq;
+        for (int64_t pl = 0; pl < nq; ++pl)
+          for (int64_t e = 0; e < m.halo_len; ++e) {
+            const int64_t d = m.halo_dst[e], s = m.halo_src[e];
+            qn2[(d / plane) * tile_stride + pl * plane + d % plane] = qn2[(s / plane) * tile_stride + pl * plane + s % plane];
+          }
+      }
+    }
+  }
+}
+
 }  // namespace fv3oracle

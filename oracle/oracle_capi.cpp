@@ -41,6 +41,25 @@ void c_tracer_2d(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mf
 }
 
 template <class T>
+void c_tracer_2d_1l(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area, const T* rarea,
+                    const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, const int64_t* halo_dst,
+                    const int64_t* halo_src, int64_t halo_len, int hord, T lim_fac, int* nsplt_out, int* ksplt_out, T* cmax_out) {
+  const long nd = n + 6;
+  std::vector<GridT<T>> g(ntiles);
+  for (int t = 0; t < ntiles; ++t) {
+    g[t].area = area + (long)t * nd * nd;
+    g[t].rarea = rarea + (long)t * nd * nd;
+    g[t].dx = dx + (long)t * nd * (nd + 1);
+    g[t].dy = dy + (long)t * (nd + 1) * nd;
+    g[t].dxa = dxa + (long)t * nd * nd;
+    g[t].dya = dya + (long)t * nd * nd;
+    g[t].sin_sg = sin_sg + (long)t * nd * nd * 5;
+  }
+  Mosaic<T> m{ntiles, n, npz, nq, q, dp1, mfx, mfy, cx, cy, g.data(), halo_dst, halo_src, halo_len};
+  tracer_2d_1L_mosaic<T>(m, hord, lim_fac, nsplt_out, ksplt_out, cmax_out);
+}
+
+template <class T>
 void c_fv_tp_2d(int n, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx, const T* yfx, const T* ra_x,
                 const T* ra_y, const T* area, const T* dxa, const T* dya, T lim_fac, const T* mfx, const T* mfy) {
   const Bounds bd = Bounds::tile(n);
@@ -145,6 +164,14 @@ void c_map_col(int which, int km, int nq, const T* pe1, const T* pe2, T* q, cons
                                         int hord, int q_split, T lim_fac, int* nsplt_out, int* ksplt_out, T* cmax_out) {      \
     c_tracer_2d<T>(ntiles, n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst, halo_src,    \
                    halo_len, hord, q_split, lim_fac, nsplt_out, ksplt_out, cmax_out);                                          \
+  }                                                                                                                            \
+  extern "C" void orc_##S##_tracer_2d_1l(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy,    \
+                                           const T* area, const T* rarea, const T* dx, const T* dy, const T* dxa,           \
+                                           const T* dya, const T* sin_sg, const int64_t* halo_dst, const int64_t* halo_src, \
+                                           int64_t halo_len, int hord, T lim_fac, int* nsplt_out, int* ksplt_out,            \
+                                           T* cmax_out) {                                                                     \
+    c_tracer_2d_1l<T>(ntiles, n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst,         \
+                      halo_src, halo_len, hord, lim_fac, nsplt_out, ksplt_out, cmax_out);                                    \
   }                                                                                                                            \
   extern "C" void orc_##S##_fv_tp_2d(int n, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx,         \
                                        const T* yfx, const T* ra_x, const T* ra_y, const T* area, const T* dxa, const T* dya, \

@@ -92,6 +92,26 @@ def tracer_2d(case, hord=8, q_split=0, lim_fac=1.0, grid_arrays=None):
     return out
 
 
+def tracer_2d_1l(case, hord=8, lim_fac=1.0):
+    """The oracle's tracer_2d_1L (fv_tracer2d.F90:92-321) on copies of a synthetic Case; same outputs as tracer_2d
+    (ksplt = the per-level sub-step counts, nsplt = their maximum)."""
+    s, ct = _sfx(case.dtype)
+    g = case.metrics()
+    out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    dst, src = halo_offsets(case.n)
+    nsplt = C.c_int(0)
+    ksplt = np.zeros(case.npz, dtype=np.int32)
+    cmax = np.zeros(case.npz, dtype=case.dtype)
+    getattr(lib(), f"orc_{s}_tracer_2d_1l")(
+        6, case.n, case.npz, case.nq, _p(out["q"]), _p(out["dp1"]), _p(out["mfx"]), _p(out["mfy"]), _p(out["cx"]),
+        _p(out["cy"]), _p(g["area"]), _p(g["rarea"]), _p(g["dx"]), _p(g["dy"]), _p(g["dxa"]), _p(g["dya"]), _p(g["sin_sg"]),
+        _p(dst), _p(src), C.c_int64(dst.size), int(hord), ct(lim_fac), C.byref(nsplt), _p(ksplt), _p(cmax))
+    out["nsplt"] = nsplt.value
+    out["ksplt"] = ksplt
+    out["cmax"] = cmax
+    return out
+
+
 def remap_tracers(q, pe, ak, bk, ptop, kord_tr, fill=True):
     """q [6, nq, km, n+6, n+6], pe [6, n+2, km+1, n+2] -> (q_out, delp_out [6, km, n+6, n+6])"""
     s, ct = _sfx(q.dtype)

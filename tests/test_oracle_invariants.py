@@ -198,3 +198,38 @@ def test_remap_positive_definite(oracle, case_factory):
     ps = case.pe[:, 1:-1, -1, 1:-1]
     dp_exp = (case.ak[1:] - case.ak[:-1])[None, :, None, None] + (case.bk[1:] - case.bk[:-1])[None, :, None, None] * ps[:, None]
     assert np.allclose(dref[..., SL, SL], dp_exp, rtol=1e-13)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("courant", [0.7, 1.8, 3.3])
+def test_tracer_2d_1l_is_bit_identical_to_tracer_2d(oracle, case_factory, courant, dtype):
+    """the level-at-a-time driver tracer_2d_1L (fv_tracer2d.F90:92-321; qn2 staging, per-level sub-step
+    count, blocking per-level halo update) and tracer_2d (:324-569) are independent restatements of two reference drivers
+    around the same fv_tp_2d; without tracer damping every output must agree bit for bit -- also the basis for serving both
+    entry points with one set of kernels."""
+    case = case_factory(12, 8, 9, dtype, courant=courant)
+    a = oracle.tracer_2d(case, hord=8)
+    b = oracle.tracer_2d_1l(case, hord=8)
+    assert b["nsplt"] == a["nsplt"] and np.array_equal(a["cmax"], b["cmax"])
+    if a["nsplt"] != 1:
+        assert np.array_equal(a["ksplt"], b["ksplt"])
+    sl = slice(3, -3)
+    assert np.array_equal(a["q"][..., sl, sl], b["q"][..., sl, sl])
+    for k in ("cx", "cy", "mfx", "mfy"):
+        assert np.array_equal(a[k], b[k]), k
+    # dp1 is the one output on which the two REFERENCE routines differ: tracer_2d copies dp2 into dp1 after every sub-step
+    # `it /= nsplt` with the GLOBAL nsplt (:547), so a level with ksplt(k) < nsplt is advanced once more after its last
+    # sub-step, while tracer_2d_1L tests the level's own count (:305).  Levels that take all nsplt sub-steps agree.
+    full = a["ksplt"] == a["nsplt"]
+    assert np.array_equal(a["dp1"][:, full][..., sl, sl], b["dp1"][:, full][..., sl, sl])
+    if (~full).any():
+        assert not np.array_equal(a["dp1"][:, ~full][..., sl, sl], b["dp1"][:, ~full][..., sl, sl])
+
+
+@pytest.mark.parametrize("hord", [10, -5, 13])
+def test_tracer_2d_1l_other_schemes(oracle, case_factory, hord):
+    case = case_factory(12, 8, 9, "float64", courant=1.8)
+    a = oracle.tracer_2d(case, hord=hord)
+    b = oracle.tracer_2d_1l(case, hord=hord)
+    sl = slice(3, -3)
+    assert np.array_equal(a["q"][..., sl, sl], b["q"][..., sl, sl])
