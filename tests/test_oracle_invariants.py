@@ -233,3 +233,56 @@ def test_tracer_2d_1l_other_schemes(oracle, case_factory, hord):
     b = oracle.tracer_2d_1l(case, hord=hord)
     sl = slice(3, -3)
     assert np.array_equal(a["q"][..., sl, sl], b["q"][..., sl, sl])
+
+
+# ---- the vertical reconstructions themselves (scalar_profile, cs_profile, ppm_profile) ---------------------------------------
+def _column(km=40, seed=3, kind="smooth"):
+    rng = np.random.default_rng(seed)
+    dp = 50.0 + 400.0 * np.sin(np.linspace(0.1, 3.0, km)) ** 2 + 5.0 * rng.random(km)
+    z = np.cumsum(dp) / dp.sum()
+    if kind == "smooth":
+        a1 = 1e-3 * (1.2 + np.sin(6.0 * z) + 0.3 * np.cos(17.0 * z))
+    elif kind == "rough":
+        a1 = 1e-3 * rng.random(km)
+        a1[rng.random(km) < 0.15] = 0.0
+    else:
+        a1 = np.where((z > 0.3) & (z < 0.6), 1e-3, 0.0)
+    return a1, dp
+
+
+@pytest.mark.parametrize("kind", ["smooth", "rough", "step"])
+@pytest.mark.parametrize("which,kords", [(0, [8, 9, 10, 11, 12, 13, 14, 15, 16, 17]), (1, [8, 9, 10, 11, 12, 13, 14, 15, 16, 17]),
+                                         (2, [1, 2, 3, 4, 5, 6, 7])])
+def test_every_profile_keeps_the_layer_mean(oracle, which, kords, kind):
+    """whatever the limiter does, the parabola it leaves has the layer mean a1:
+    (a2 + a3)/2 + a4/6 == a1 (fv_mapz.F90 scalar_profile / cs_profile / ppm_profile all end in a4 = 3(2 a1 - (a2 + a3)))."""
+    a1, dp = _column(kind=kind)
+    for kord in kords:
+        a4 = oracle.profile_col(which, a1, dp, iv=0, kord=kord)
+        assert np.array_equal(a4[:, 0], a1)
+        mean = 0.5 * (a4[:, 1] + a4[:, 2]) + a4[:, 3] / 6.0
+        assert np.abs(mean - a1).max() <= 4e-16 * max(np.abs(a1).max(), 1e-300) + 1e-19, (which, kord, np.abs(mean - a1).max())
+
+
+@pytest.mark.parametrize("kord", [8, 9, 10, 11, 12, 13, 14, 15, 16])
+def test_positive_definite_profiles_stay_non_negative(oracle, kord):
+    """iv = 0 (tracers): cs_limiters(iv=0) leaves a parabola whose minimum over the layer is >= 0 for non-negative means
+    (fv_mapz.F90:2501-2530)."""
+    for kind in ("smooth", "rough", "step"):
+        a1, dp = _column(kind=kind)
+        for which in (0, 1):
+            a4 = oracle.profile_col(which, a1, dp, iv=0, kord=kord)
+            a2, a3, a6 = a4[:, 1], a4[:, 2], a4[:, 3]
+            x = np.linspace(0.0, 1.0, 65)[None, :]
+            prof = a2[:, None] + x * ((a3 - a2)[:, None] + a6[:, None] * (1.0 - x))
+            assert prof.min() >= -1e-18, (kind, which, kord, prof.min())
+
+
+@pytest.mark.parametrize("kord", [10, 12, 13, 14, 16])
+def test_scalar_profile_and_cs_profile_agree_where_they_share_the_algorithm(oracle, kord):
+    """scalar_profile (the tracers' routine) and cs_profile differ only in the qmin tests of kord 9/11/15 and in rounding
+    (SURVEY.md 'two different roundings'): for the other limiters they agree to rounding on positive data."""
+    a1, dp = _column(kind="smooth")
+    s = oracle.profile_col(0, a1, dp, iv=0, kord=kord)
+    c = oracle.profile_col(1, a1, dp, iv=0, kord=kord)
+    assert np.abs(s - c).max() <= 1e-12 * np.abs(a1).max()
