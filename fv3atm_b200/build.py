@@ -13,8 +13,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfv3tracer.so")
 # Two translation units: the strict kernels + host orchestration keep the bit-exact contract with the FMA-free oracle
 # (no contraction, IEEE division/sqrt); the production kernels (fv3t_fast.cu) are built with FMA contraction on.
-SOURCES = {"fv3t_api.cu": ["--fmad=false"], "fv3t_fast.cu": ["--fmad=true"]}
-HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_remap.cuh",
+# The fast TU is compiled once per precision (two objects, in parallel): its k_advect5 instantiations dominate the build time.
+SOURCES = [("fv3t_api.cu", "fv3t_api.o", ["--fmad=false"]),
+           ("fv3t_fast.cu", "fv3t_fast_f64.o", ["--fmad=true", "-DFV3T_INST_F64"]),
+           ("fv3t_fast.cu", "fv3t_fast_f32.o", ["--fmad=true", "-DFV3T_INST_F32"])]
+HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_advect5.cuh", "fv3t_remap.cuh",
            "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
 
 NVCC_FLAGS = [
@@ -34,7 +37,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in list(SOURCES) + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "fv3tracer.h")]
+    deps = [os.path.join(CSRC, f) for f in [x[0] for x in SOURCES] + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "fv3tracer.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -43,8 +46,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     env = dict(os.environ)
     procs = []
-    for src, extra in SOURCES.items():
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+    dev = ["-DFV3T_A5_DEV"] if os.environ.get("FV3T_A5_DEV") else []  # development builds: k_advect5 for hord 8 / 10 only
+    for src, objname, extra in SOURCES:
+        obj = os.path.join(CSRC, objname)
+        extra = extra + dev
         cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((obj, subprocess.Popen(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []

@@ -119,13 +119,169 @@ template <class T> FV3T_HD T dm_of(T qm, T q0, T qp) {
   const T xt = T(0.25) * (qp - qm);
   const bool up = qm < qp;
   const T lo = up ? qm : qp, hi = up ? qp : qm;
-  const T m = f_max(f_min(hi - q0, q0 - lo), T(0));
-  return f_sign(f_min(f_abs(xt), m), xt);
+  return dm_limit<T>(xt, f_min(hi - q0, q0 - lo));
 }
 
 // two-sided edge value between cells (a, b | c, d) with metric (ma, mb | mc, md)  (tp_core.F90:384-385, 640-641)
 template <class T> FV3T_HD T edge_value4(T qa, T qb, T qc, T qd, T ma, T mb, T mc, T md) {
   return T(0.5) * (((T(2) * mb + ma) * qb - mb * qa) / (ma + mb) + ((T(2) * mc + md) * qc - mc * qd) / (mc + md));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Rolling 1-D PPM state of one column (yppm restated cell by cell).  When row r arrives the cell c = r-2 is
+// reconstructed (its stencil q(c-2..c+2) is complete) and the flux at face c (between cells c-1 and c) is returned.
+// ---------------------------------------------------------------------------------------------------------------------
+// One step of the rolling 1-D PPM reconstruction of a column (yppm restated cell by cell): with q(c-2..c+2) and the carried
+// quantities of cells c-1, c in hand, reconstruct cell c and return the flux at face c (between cells c-1 and c).
+// EDGE = false compiles the tile-edge formulas (and the tests that select them) out: the caller guarantees 3 <= c <= npx-3
+// (ORD >= 7) resp. 3 <= c+1 <= npx-2 (ORD < 7).  Outputs: a_p1 = dm(c+1) / al(c+1), al_p1 = al(c+1) (ORD >= 7), bl/br/fl of
+// cell c; xt, xt2 carry the tile-edge values across the three edge cells.
+template <class T, int ORD, bool EDGE, class MF>
+FV3T_HD T ystream_core(int c, T qm2, T qm1, T q0, T qp1, T qp2, T a_m1, T a_0, T al_0, T bl_m1, T br_m1, int fl_m1, T& xt, T& xt2,
+                       T cour, int npx, T lim_fac, MF met, T& a_p1, T& al_p1, T& bl, T& br, int& fl) {
+  constexpr int mord = ORD < 0 ? -ORD : ORD;
+  bl = T(0);
+  br = T(0);
+  fl = 0;
+  al_p1 = T(0);
+  if (ORD >= 7) {
+    a_p1 = dm_of<T>(q0, qp1, qp2);
+    al_p1 = T(0.5) * (q0 + qp1) + K<T>::r3() * (a_0 - a_p1);
+    if (!EDGE || (c >= 3 && c <= npx - 3)) {
+      const T qm = qm1, qp = qp1, dm0 = a_0;
+      const T al0 = al_0, al1 = al_p1;
+      if (ORD == 8 || ORD == 11) {
+        const T x = (ORD == 8 ? T(2) : K<T>::ppm_fac()) * dm0;
+        bl = -sign_min_abs<T>(x, al0 - q0);
+        br = sign_min_abs<T>(x, al1 - q0);
+      } else if (ORD == 10) {
+        bl = al0 - q0;
+        br = al1 - q0;
+        if (f_abs(a_m1) + f_abs(dm0) + f_abs(a_p1) < K<T>::near_zero()) {
+          bl = T(0);
+          br = T(0);
+        } else if (f_abs(T(3) * (bl + br)) > f_abs(bl - br)) {
+          const T dq_m2 = T(2) * (qm - qm2);
+          const T dq_m1 = T(2) * (q0 - qm);
+          const T dq_0 = T(2) * (qp - q0);
+          const T dq_p1 = T(2) * (qp2 - qp);
+          const T pmp_2 = dq_m1;
+          const T lac_2 = pmp_2 - T(0.75) * dq_m2;
+          br = f_min(f_max(T(0), pmp_2, lac_2), f_max(br, f_min(T(0), pmp_2, lac_2)));
+          const T pmp_1 = -dq_0;
+          const T lac_1 = pmp_1 + T(0.75) * dq_p1;
+          bl = f_min(f_max(T(0), pmp_1, lac_1), f_max(bl, f_min(T(0), pmp_1, lac_1)));
+        }
+      } else if (ORD == 7 || ORD == 12) {
+        bl = al0 - q0;
+        br = al1 - q0;
+        const T a4 = T(-3) * (bl + br);
+        const T da1 = br - bl;
+        const bool ext5 = br * bl > T(0);
+        const bool ext6 = f_abs(da1) < -a4;
+        if (ext6) {
+          if (q0 + T(0.25) / a4 * (da1 * da1) + a4 * K<T>::r12() < T(0)) {
+            if (ext5) {
+              br = T(0);
+              bl = T(0);
+            } else if (da1 > T(0)) {
+              br = T(-2) * bl;
+            } else {
+              bl = T(-2) * br;
+            }
+          }
+        }
+      } else {
+        bl = al0 - q0;
+        br = al1 - q0;
+        if (ORD == 9 || ORD == 13) pert_ppm1<T>(q0, bl, br, 0);
+      }
+    } else if (c >= 0 && c <= npx) {
+      // tile-edge cells 0,1,2 and npx-2,npx-1,npx (tp_core.F90:636-674 with i <-> j)
+      if (c == 0 || c == npx - 1) {
+        // e0 = c+1: couples cells (c-1, c | c+1, c+2)
+        T x = edge_value4<T>(qm1, q0, qp1, qp2, met(c - 1), met(c), met(c + 1), met(c + 2));
+        x = f_max(x, f_min(qm1, q0, qp1, qp2));
+        x = f_min(x, f_max(qm1, q0, qp1, qp2));
+        if (c == 0) {
+          bl = K<T>::s14() * a_m1 + K<T>::s11() * (qm1 - q0);
+          br = x - q0;
+        } else {
+          bl = xt2 - q0;
+          br = x - q0;
+        }
+        xt = x;
+      } else if (c == 1) {
+        xt2 = K<T>::s15() * q0 + K<T>::s11() * qp1 - K<T>::s14() * a_p1;
+        bl = xt - q0;
+        br = xt2 - q0;
+      } else if (c == 2) {
+        bl = xt2 - q0;
+        br = al_p1 - q0;
+      } else if (c == npx - 2) {
+        xt2 = K<T>::s15() * qp1 + K<T>::s11() * q0 + K<T>::s14() * a_0;
+        bl = al_0 - q0;
+        br = xt2 - q0;
+      } else {  // c == npx
+        bl = xt - q0;
+        br = K<T>::s11() * (qp1 - q0) - K<T>::s14() * a_p1;
+      }
+      pert_ppm1<T>(q0, bl, br, 1);
+    }
+  } else {
+    // al(c+1) (tp_core.F90:377-400 with i <-> j)
+    const int f = c + 1;
+    if (EDGE && (f == 0 || f == npx - 1))
+      a_p1 = K<T>::c1() * qm1 + K<T>::c2() * q0 + K<T>::c3() * qp1;
+    else if (EDGE && (f == 1 || f == npx))
+      a_p1 = edge_value4<T>(qm1, q0, qp1, qp2, met(c - 1), met(c), met(c + 1), met(c + 2));
+    else if (EDGE && (f == 2 || f == npx + 1))
+      a_p1 = K<T>::c3() * q0 + K<T>::c2() * qp1 + K<T>::c1() * qp2;
+    else
+      a_p1 = K<T>::p1() * (q0 + qp1) + K<T>::p2() * (qm1 + qp2);
+    if (ORD < 0) a_p1 = f_max(T(0), a_p1);
+    bl = a_0 - q0;
+    br = a_p1 - q0;
+    const T b0 = bl + br;
+    if (mord == 1) {
+      fl = f_abs(lim_fac * b0) < f_abs(bl - br);
+    } else if (mord == 3 || mord == 4) {
+      const T x0 = f_abs(b0);
+      const T x1 = f_abs(bl - br);
+      fl = (x0 < x1 ? 1 : 0) | (T(3) * x0 < x1 ? 2 : 0);
+    } else if (ORD == 5) {
+      fl = bl * br < T(0);
+    } else if (ORD == -5) {
+      fl = bl * br < T(0);
+      const T da1 = br - bl;
+      const T a4 = T(-3) * b0;
+      if (f_abs(da1) < -a4) {
+        if (q0 + T(0.25) * (da1 * da1) / a4 + a4 * K<T>::r12() < T(0)) {
+          if (!fl) {
+            br = T(0);
+            bl = T(0);
+          } else if (da1 > T(0)) {
+            br = T(-2) * bl;
+          } else {
+            bl = T(-2) * br;
+          }
+        }
+      }
+    } else if (mord != 2) {
+      fl = f_abs(T(3) * b0) < f_abs(bl - br);
+    }
+  }
+  // flux at face c
+  const T qm1_ = qm1, q0_ = q0, blm = bl_m1, brm = br_m1;
+  const T bl_ = bl, br_ = br;
+  const int flm = fl_m1, fl_ = fl;
+  const T alm = a_m1, al0_ = a_0, alp = a_p1;
+  auto fq = [&](int gi) -> T { return gi == c ? q0_ : qm1_; };
+  auto fbl = [&](int gi) -> T { return gi == c ? bl_ : blm; };
+  auto fbr = [&](int gi) -> T { return gi == c ? br_ : brm; };
+  auto ffl = [&](int gi) -> int { return gi == c ? fl_ : flm; };
+  auto fal = [&](int gi) -> T { return gi == c ? al0_ : (gi == c - 1 ? alm : alp); };
+  return ppm_flux<T, ORD>(c, cour, fq, fbl, fbr, ffl, fal);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -147,148 +303,10 @@ template <class T, int ORD> struct YStream {
 
   // met(row) = metric along the sweep (dya(i,row)), read only at the tile edges.  q_cm1 returns q(c-1).
   template <class MF> FV3T_HD T push(int c, T qp2, T cour, int npx, T lim_fac, MF met, T& q_cm1) {
-    constexpr int mord = ORD < 0 ? -ORD : ORD;
-    T bl = T(0), br = T(0);
-    int fl = 0;
-    T a_p1;  // dm(c+1) or al(c+1)
-    T al_p1 = T(0);
-    if (ORD >= 7) {
-      a_p1 = dm_of<T>(q0, qp1, qp2);
-      al_p1 = T(0.5) * (q0 + qp1) + K<T>::r3() * (a_0 - a_p1);
-      if (c >= 3 && c <= npx - 3) {
-        const T qm = qm1, qp = qp1, dm0 = a_0;
-        const T al0 = al_0, al1 = al_p1;
-        if (ORD == 8 || ORD == 11) {
-          const T x = (ORD == 8 ? T(2) : K<T>::ppm_fac()) * dm0;
-          bl = -f_sign(f_min(f_abs(x), f_abs(al0 - q0)), x);
-          br = f_sign(f_min(f_abs(x), f_abs(al1 - q0)), x);
-        } else if (ORD == 10) {
-          bl = al0 - q0;
-          br = al1 - q0;
-          if (f_abs(a_m1) + f_abs(dm0) + f_abs(a_p1) < K<T>::near_zero()) {
-            bl = T(0);
-            br = T(0);
-          } else if (f_abs(T(3) * (bl + br)) > f_abs(bl - br)) {
-            const T dq_m2 = T(2) * (qm - qm2);
-            const T dq_m1 = T(2) * (q0 - qm);
-            const T dq_0 = T(2) * (qp - q0);
-            const T dq_p1 = T(2) * (qp2 - qp);
-            const T pmp_2 = dq_m1;
-            const T lac_2 = pmp_2 - T(0.75) * dq_m2;
-            br = f_min(f_max(T(0), pmp_2, lac_2), f_max(br, f_min(T(0), pmp_2, lac_2)));
-            const T pmp_1 = -dq_0;
-            const T lac_1 = pmp_1 + T(0.75) * dq_p1;
-            bl = f_min(f_max(T(0), pmp_1, lac_1), f_max(bl, f_min(T(0), pmp_1, lac_1)));
-          }
-        } else if (ORD == 7 || ORD == 12) {
-          bl = al0 - q0;
-          br = al1 - q0;
-          const T a4 = T(-3) * (bl + br);
-          const T da1 = br - bl;
-          const bool ext5 = br * bl > T(0);
-          const bool ext6 = f_abs(da1) < -a4;
-          if (ext6) {
-            if (q0 + T(0.25) / a4 * (da1 * da1) + a4 * K<T>::r12() < T(0)) {
-              if (ext5) {
-                br = T(0);
-                bl = T(0);
-              } else if (da1 > T(0)) {
-                br = T(-2) * bl;
-              } else {
-                bl = T(-2) * br;
-              }
-            }
-          }
-        } else {
-          bl = al0 - q0;
-          br = al1 - q0;
-          if (ORD == 9 || ORD == 13) pert_ppm1<T>(q0, bl, br, 0);
-        }
-      } else if (c >= 0 && c <= npx) {
-        // tile-edge cells 0,1,2 and npx-2,npx-1,npx (tp_core.F90:636-674 with i <-> j)
-        if (c == 0 || c == npx - 1) {
-          // e0 = c+1: couples cells (c-1, c | c+1, c+2)
-          T x = edge_value4<T>(qm1, q0, qp1, qp2, met(c - 1), met(c), met(c + 1), met(c + 2));
-          x = f_max(x, f_min(qm1, q0, qp1, qp2));
-          x = f_min(x, f_max(qm1, q0, qp1, qp2));
-          if (c == 0) {
-            bl = K<T>::s14() * a_m1 + K<T>::s11() * (qm1 - q0);
-            br = x - q0;
-          } else {
-            bl = xt2 - q0;
-            br = x - q0;
-          }
-          xt = x;
-        } else if (c == 1) {
-          xt2 = K<T>::s15() * q0 + K<T>::s11() * qp1 - K<T>::s14() * a_p1;
-          bl = xt - q0;
-          br = xt2 - q0;
-        } else if (c == 2) {
-          bl = xt2 - q0;
-          br = al_p1 - q0;
-        } else if (c == npx - 2) {
-          xt2 = K<T>::s15() * qp1 + K<T>::s11() * q0 + K<T>::s14() * a_0;
-          bl = al_0 - q0;
-          br = xt2 - q0;
-        } else {  // c == npx
-          bl = xt - q0;
-          br = K<T>::s11() * (qp1 - q0) - K<T>::s14() * a_p1;
-        }
-        pert_ppm1<T>(q0, bl, br, 1);
-      }
-    } else {
-      // al(c+1) (tp_core.F90:377-400 with i <-> j)
-      const int f = c + 1;
-      if (f == 0 || f == npx - 1)
-        a_p1 = K<T>::c1() * qm1 + K<T>::c2() * q0 + K<T>::c3() * qp1;
-      else if (f == 1 || f == npx)
-        a_p1 = edge_value4<T>(qm1, q0, qp1, qp2, met(c - 1), met(c), met(c + 1), met(c + 2));
-      else if (f == 2 || f == npx + 1)
-        a_p1 = K<T>::c3() * q0 + K<T>::c2() * qp1 + K<T>::c1() * qp2;
-      else
-        a_p1 = K<T>::p1() * (q0 + qp1) + K<T>::p2() * (qm1 + qp2);
-      if (ORD < 0) a_p1 = f_max(T(0), a_p1);
-      bl = a_0 - q0;
-      br = a_p1 - q0;
-      const T b0 = bl + br;
-      if (mord == 1) {
-        fl = f_abs(lim_fac * b0) < f_abs(bl - br);
-      } else if (mord == 3 || mord == 4) {
-        const T x0 = f_abs(b0);
-        const T x1 = f_abs(bl - br);
-        fl = (x0 < x1 ? 1 : 0) | (T(3) * x0 < x1 ? 2 : 0);
-      } else if (ORD == 5) {
-        fl = bl * br < T(0);
-      } else if (ORD == -5) {
-        fl = bl * br < T(0);
-        const T da1 = br - bl;
-        const T a4 = T(-3) * b0;
-        if (f_abs(da1) < -a4) {
-          if (q0 + T(0.25) * (da1 * da1) / a4 + a4 * K<T>::r12() < T(0)) {
-            if (!fl) {
-              br = T(0);
-              bl = T(0);
-            } else if (da1 > T(0)) {
-              br = T(-2) * bl;
-            } else {
-              bl = T(-2) * br;
-            }
-          }
-        }
-      } else if (mord != 2) {
-        fl = f_abs(T(3) * b0) < f_abs(bl - br);
-      }
-    }
-    // flux at face c
-    const T qm1_ = qm1, q0_ = q0, blm = bl_m1, brm = br_m1;
-    const int flm = fl_m1;
-    const T alm = a_m1, al0_ = a_0, alp = a_p1;
-    auto fq = [&](int gi) -> T { return gi == c ? q0_ : qm1_; };
-    auto fbl = [&](int gi) -> T { return gi == c ? bl : blm; };
-    auto fbr = [&](int gi) -> T { return gi == c ? br : brm; };
-    auto ffl = [&](int gi) -> int { return gi == c ? fl : flm; };
-    auto fal = [&](int gi) -> T { return gi == c ? al0_ : (gi == c - 1 ? alm : alp); };
-    const T flux = ppm_flux<T, ORD>(c, cour, fq, fbl, fbr, ffl, fal);
+    T a_p1, al_p1, bl, br;
+    int fl;
+    const T flux = ystream_core<T, ORD, true>(c, qm2, qm1, q0, qp1, qp2, a_m1, a_0, al_0, bl_m1, br_m1, fl_m1, xt, xt2, cour, npx, lim_fac,
+                                              met, a_p1, al_p1, bl, br, fl);
     q_cm1 = qm1;
     // shift to cell c+1
     qm2 = qm1;
@@ -305,23 +323,65 @@ template <class T, int ORD> struct YStream {
   }
 };
 
+// The same stream with its windows held in phase-indexed slots: step PH = (row step) mod 4 reads q(c-2..c+1) from slots
+// PH..PH+3 (mod 4) and overwrites slot PH with the new row, so that a row loop unrolled by four rotates the windows by
+// renaming only -- no register moves (they were 88 of the 710 instructions per cell-update of k_advect4,
+// profiles/r01_advect4_c384_ncu.txt).
+template <class T, int ORD> struct YWin {
+  T q[4];
+  T a[2];
+  T al_0, bl_m1, br_m1;
+  int fl_m1;
+  FV3T_HD void init() {
+    for (int k = 0; k < 4; ++k) q[k] = T(0);
+    a[0] = a[1] = al_0 = bl_m1 = br_m1 = T(0);
+    fl_m1 = 0;
+  }
+  // q(c-1) before the push = q(o) of the marching kernels' output row after it
+  template <int PH> FV3T_HD T q_cm1() const { return q[(PH + 1) & 3]; }
+  // edge2: two per-thread scratch slots (stride `es` elements) that carry the tile-edge values xt, xt2 across the three edge
+  // cells; touched only by the EDGE instantiation, so the interior row loop does not keep them in registers
+  template <int PH, bool EDGE, class MF> FV3T_HD T push(int c, T qp2, T cour, int npx, T lim_fac, MF met, T* edge2, int es) {
+    T a_p1, al_p1, bl, br;
+    int fl;
+    T xt = T(0), xt2 = T(0);
+    if (EDGE) {
+      xt = edge2[0];
+      xt2 = edge2[es];
+    }
+    const T flux = ystream_core<T, ORD, EDGE>(c, q[PH & 3], q[(PH + 1) & 3], q[(PH + 2) & 3], q[(PH + 3) & 3], qp2, a[PH & 1], a[(PH + 1) & 1],
+                                              al_0, bl_m1, br_m1, fl_m1, xt, xt2, cour, npx, lim_fac, met, a_p1, al_p1, bl, br, fl);
+    if (EDGE) {
+      edge2[0] = xt;
+      edge2[es] = xt2;
+    }
+    q[PH & 3] = qp2;
+    a[PH & 1] = a_p1;
+    al_0 = al_p1;
+    bl_m1 = bl;
+    br_m1 = br;
+    fl_m1 = fl;
+    return flux;
+  }
+};
+
 // flux at x-face i from a row held in shared memory: q(gi), a(gi) (dm for ORD >= 7, al for ORD < 7) by global index
-template <class T, int ORD, class QF, class AF, class DF>
+template <class T, int ORD, bool EDGE = true, class QF, class AF, class DF>
 FV3T_HD T xface_flux(int i, T cour, int npx, T lim_fac, QF q, AF a, DF dxa) {
   if (ORD >= 8) {
     const bool up = cour > T(0);
     const int u = up ? i - 1 : i;
     T bl, br;
     int flg;
-    ppm_blbr<T, ORD>(u, npx, q, a, dxa, lim_fac, bl, br, flg);
+    ppm_blbr<T, ORD, EDGE>(u, npx, q, a, dxa, lim_fac, bl, br, flg);
     const T qu = q(u);
     const T a = f_abs(cour);  // see ppm_flux: one expression for both wind directions, bit-identical to the reference's two
     return qu + (T(1) - a) * ((up ? br : bl) - a * (bl + br));
   } else {
     T blm, brm, bl0, br0;
     int fm, f0;
-    ppm_blbr<T, ORD>(i - 1, npx, q, a, dxa, lim_fac, blm, brm, fm);
-    ppm_blbr<T, ORD>(i, npx, q, a, dxa, lim_fac, bl0, br0, f0);
+    ppm_blbr<T, ORD, EDGE>(i - 1, npx, q, a, dxa, lim_fac, blm, brm, fm);
+    ppm_blbr<T, ORD, EDGE>(i, npx, q, a, dxa, lim_fac, bl0, br0, f0);
     auto fbl = [&](int gi) -> T { return gi == i ? bl0 : blm; };
     auto fbr = [&](int gi) -> T { return gi == i ? br0 : brm; };
     auto ffl = [&](int gi) -> int { return gi == i ? f0 : fm; };

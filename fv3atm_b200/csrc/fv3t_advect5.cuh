@@ -1,0 +1,548 @@
+// fv3atm_b200: multi-tracer marching advection CTA with TMA-staged level fields (sm_100a).
+//
+// Same operator as fv3t_advect3/4.cuh (one tracer_2d sub-step, atmos_cubed_sphere/model/fv_tracer2d.F90:503-556 -> fv_tp_2d,
+// model/tp_core.F90:110-249 with xppm :332-704, yppm :707-1124, copy_corners :253-330, pert_ppm :1178-1236) and the same
+// per-element arithmetic (fv3t_ppm.cuh, ystream_core).  What changes is the decomposition:
+//   * one CTA = one 58-column strip of one (tile, level) for UP TO TEN TRACERS: warp 0 is a TMA producer, every following
+//     pair of warps (64 threads, one column each) marches one tracer over the rows of the tile.  The tracer-independent level
+//     fields ({cx,xfx}, {cy,yfx}, 1/ra_x, 1/ra_y, mfx, mfy, area, {dp1/dp2, rarea/2dp2}) are fetched ONCE per strip and
+//     level -- not once per tracer -- by cp.async.bulk.tensor (UTMALDG) into a three-stage shared-memory ring of four-row
+//     boxes, completion on mbarriers; k_advect4 issued eleven per-thread LDGSTS plus their address arithmetic per tracer-cell
+//     and moved 2.1x the algorithmic bytes through DRAM (profiles/r01_advect4_c384_ncu.txt, r01_traffic_c768.json).
+//   * the row loop is unrolled by four with phase-indexed windows (YWin): the rolling y-stream windows and the delayed inner
+//     x flux rotate by renaming, not by register moves.
+//   * rows / strips away from the tile edges run instantiations with the tile-edge formulas, the corner views of q and all
+//     row clamps compiled out.
+//   * the two-warp group of a tracer synchronises on its own named barrier; the groups of a CTA drift apart freely.
+// The per-thread phase functions run unchanged on the host (tests/hostsim/advect5_hostsim.cu, test infrastructure).
+#pragma once
+#include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved at run time in fv3t_fast.cu)
+
+#include "fv3t_advect4.cuh"
+
+namespace fv3t {
+
+constexpr int A5_R = 4;    // row steps per staged box
+constexpr int A5_NS = 3;   // stages of the ring
+constexpr int A5_GW = 64;  // threads (columns) per tracer group: 58 compute columns + 3 halo columns either side
+constexpr int A5_W = A5_GW - 6;
+constexpr int A5_XP = A5_GW + 8;  // pitch of an exchange row (4 pad slots either side)
+constexpr int A5_XPAD = 4;
+constexpr int A5_XROWS = 7;  // 0,1 q of row r (by row parity)  2 dm/al of row r  3 q_i of row o  4 dm/al of row o  5 xfx*fx2  6 (fx+fx2)*mfx
+constexpr int A5_MAXTG = 9;   // 1 + 2*9 = 19 warps -> 96 registers per thread at one CTA per SM
+
+// padded row pitch of the scratch planes: a multiple of 16 bytes in fp32 and fp64 (TMA global strides)
+FV3T_HD int a5_pitch(int n) { return (n + 6 + 3) & ~3; }
+
+// staged arrays of one box (A5_R rows x A5_GW columns each)
+enum : int { A5_XR = 0, A5_XO = 1, A5_Y2 = 2, A5_CAB = 3, A5_NPAIR = 4 };                           // Pair<T>
+enum : int { A5_RX = 0, A5_MFX = 1, A5_RY = 2, A5_MFY = 3, A5_AR = 4, A5_AO = 5, A5_NSC = 6 };      // T
+template <class T> struct A5Stage {
+  static constexpr int PAIR_BYTES = A5_NPAIR * A5_R * A5_GW * 2 * (int)sizeof(T);
+  static constexpr int BYTES = PAIR_BYTES + A5_NSC * A5_R * A5_GW * (int)sizeof(T);
+  // exchange rows + per-thread private slots: 2 qy (corner rows), 4 delayed inner x fluxes, 2x2 tile-edge values of the y streams
+  static constexpr int PRIV = 10;
+  static constexpr int GROUP_ELEMS = A5_XROWS * A5_XP + PRIV * A5_GW;
+  static constexpr int BAR_OFF = A5_NS * BYTES;
+  static constexpr int GROUP_OFF = BAR_OFF + 128;
+  static size_t smem_bytes(int tg) { return (size_t)GROUP_OFF + (size_t)tg * GROUP_ELEMS * sizeof(T); }
+};
+
+struct alignas(64) Adv5Maps {
+  CUtensorMap x2, y2, cab, rx, ry, mfx, mfy, area;
+};
+
+template <class T> struct Adv5Params {
+  const T* qin;
+  T* qout;
+  // scratch of the resident level chunk, padded plane layout [level][row 0..nd-1][PP] (row = j+2, column = i+2)
+  const Pair<T>*X2, *Y2, *CAB;
+  const T *RX, *RY, *MFX, *MFY;
+  const T* AREA;        // [tile][nd][PP]
+  const T *dxa, *dya;   // Fortran layout (tile-edge formulas only)
+  const int* ksplt;
+  int n, npz, nq, ntiles, it;
+  int lev0;             // global level (tile*npz + kz) of chunk level 0
+  int tg;               // tracers per CTA (block = 32 + 64*tg threads)
+  int iq0, nql;         // this launch advects tracers iq0 .. iq0+nql-1
+  T lim_fac;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_prep5: the tracer-independent part of one sub-step for a chunk of levels (fv_tracer2d.F90:387-405 xfx/yfx, :449-486
+// frac scaling, :510-526 dp2 / ra_x / ra_y, :547-553 dp1 <- dp2).  Reads the UNSCALED cx, cy, mfx, mfy (k_scale3 scales them
+// in place when the call finishes).  mode_all = 0 (it > 1, scratch holds every level): only dp1 and CAB are refreshed.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T> struct Prep5Params {
+  const T *cx, *cy, *mfx, *mfy;
+  T* dp1;
+  GridDev<T> g;
+  Pair<T>*X2, *Y2, *CAB;
+  T *RX, *RY, *MFX, *MFY;
+  const int* ksplt;
+  int n, npz, ntiles, lev0, nlev, it, mode_all;
+};
+
+template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, int e) {
+  const int n = p.n, nd = n + 6, PP = a5_pitch(n);
+  const long plane = (long)nd * nd;
+  const long lev = p.lev0 + levc;
+  const int t = (int)(lev / p.npz), kz = (int)(lev % p.npz);
+  const int ks = p.ksplt[kz];
+  if (p.it - 1 > ks) return;  // the level took no part in sub-step it-1: nothing changes any more
+  const int j = e / nd - 2, i = e % nd - 2;
+  const T frac = T(1) / (T)ks;
+  const T* area = p.g.area + (long)t * plane;
+  const T* rarea = p.g.rarea + (long)t * plane;
+  const T* mxp = p.mfx + lev * (long)(n + 1) * n;
+  const T* myp = p.mfy + lev * (long)n * (n + 1);
+  const long o = ((long)levc * nd + (j + 2)) * PP + (i + 2);
+  const bool cell = i >= 1 && i <= n && j >= 1 && j <= n;
+  Pair<T> ab{T(0), T(0)};
+  if (cell) {
+    const long ox = (long)(j - 1) * (n + 1) + (i - 1), oy = (long)(j - 1) * n + (i - 1);
+    const T rar = rarea[e];
+    const T m0 = mul_rn(mxp[ox], frac), m1 = mul_rn(mxp[ox + 1], frac), m2 = mul_rn(myp[oy], frac), m3 = mul_rn(myp[oy + n], frac);
+    T d1 = p.dp1[lev * plane + e];
+    if (p.it > 1) {  // dp1 <- dp2 of sub-step it-1 (fv_tracer2d.F90:547-553)
+      d1 = dp2_of<T>(d1, m0, m1, m2, m3, rar);
+      p.dp1[lev * plane + e] = d1;
+    }
+    if (p.it <= ks) {
+      const T d2 = dp2_of<T>(d1, m0, m1, m2, m3, rar);
+      const T r2 = T(1) / d2;
+      ab.a = d1 * r2;
+      ab.b = T(0.5) * rar * r2;
+    }
+  }
+  if (p.it > ks) return;
+  p.CAB[o] = ab;
+  if (!p.mode_all) return;
+  const T* dxa = p.g.dxa + (long)t * plane;
+  const T* dya = p.g.dya + (long)t * plane;
+  const T* dxg = p.g.dx + (long)t * nd * (nd + 1);
+  const T* dyg = p.g.dy + (long)t * (nd + 1) * nd;
+  const T* ssg = p.g.sin_sg + (long)t * plane * 5;
+  const T* cxp = p.cx + lev * (long)(n + 1) * nd;
+  const T* cyp = p.cy + lev * (long)nd * (n + 1);
+  Pair<T> x2{T(0), T(0)}, y2{T(0), T(0)};
+  T rx = T(0), ry = T(0), mx = T(0), my = T(0);
+  if (i >= 1 && i <= n + 1) {
+    T c;
+    const T xf = xfx_of<T>(cxp, dxa, dyg, ssg, plane, nd, n, i, j, frac, c);
+    x2.a = mul_rn(c, frac);
+    x2.b = xf;
+    if (i <= n) {
+      T c1;
+      const T xf1 = xfx_of<T>(cxp, dxa, dyg, ssg, plane, nd, n, i + 1, j, frac, c1);
+      rx = T(1) / add_rn(add_rn(area[e], xf), -xf1);
+    }
+    if (j >= 1 && j <= n) mx = mul_rn(mxp[(long)(j - 1) * (n + 1) + (i - 1)], frac);
+  }
+  if (j >= 1 && j <= n + 1) {
+    T c;
+    const T yf = yfx_of<T>(cyp, dya, dxg, ssg, plane, nd, n, i, j, frac, c);
+    y2.a = mul_rn(c, frac);
+    y2.b = yf;
+    if (j <= n) {
+      T c1;
+      const T yf1 = yfx_of<T>(cyp, dya, dxg, ssg, plane, nd, n, i, j + 1, frac, c1);
+      ry = T(1) / add_rn(add_rn(area[e], yf), -yf1);
+    }
+    if (i >= 1 && i <= n) my = mul_rn(myp[(long)(j - 1) * n + (i - 1)], frac);
+  }
+  p.X2[o] = x2;
+  p.Y2[o] = y2;
+  p.RX[o] = rx;
+  p.RY[o] = ry;
+  p.MFX[o] = mx;
+  p.MFY[o] = my;
+}
+
+#ifdef __CUDACC__
+template <class T> __global__ void __launch_bounds__(256) k_prep5(const Prep5Params<T> p) {
+  const int nd = p.n + 6;
+  const int total = nd * nd;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) prep5_cell<T>(p, blockIdx.y, e);
+}
+// padded copy of a 2-D metric array: dst [tile][nd][PP] <- src [tile][nd][nd]
+template <class T> __global__ void __launch_bounds__(256) k_pad_plane(T* __restrict__ dst, const T* __restrict__ src, int nd, int PP, int ntiles) {
+  const long total = (long)ntiles * nd * PP;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int col = (int)(e % PP);
+    const long row = e / PP;
+    dst[e] = col < nd ? src[row * nd + col] : T(0);
+  }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the marching group
+// ---------------------------------------------------------------------------------------------------------------------
+struct Adv5Cta {  // uniform over one tracer group
+  int n, npx, nd, i0, nw, gb;
+  int tile, tileoff;  // element offset of this tile in the Fortran-layout 2-D metric arrays
+  long qoff;          // element offset of the (tile, tracer, level) plane of q
+  bool xedge;         // the strip touches the west or east tile edge
+};
+
+template <class T> FV3T_HD bool adv5_make_cta(const Adv5Params<T>& p, int strip, int levc, int iq, Adv5Cta& c) {
+  const int n = p.n, npz = p.npz;
+  const int lev = p.lev0 + levc;
+  const int t = lev / npz, kz = lev % npz;
+  if (p.it > p.ksplt[kz]) return false;
+  const int nd = n + 6;
+  c.n = n;
+  c.npx = n + 1;
+  c.nd = nd;
+  c.i0 = 1 + strip * A5_W;
+  c.nw = (A5_W < n - c.i0 + 1) ? A5_W : n - c.i0 + 1;
+  c.gb = c.i0 - 3;
+  c.tile = t;
+  c.tileoff = t * nd * nd;
+  c.qoff = (((long)t * p.nq + iq) * npz + kz) * (long)nd * nd;
+  // x-faces i0 .. i0+nw evaluate cells i0-1 .. i0+nw; the tile-edge formulas apply to cells <= 2 and >= npx-2
+  c.xedge = (c.i0 - 1 <= 2) || (c.i0 + c.nw >= c.npx - 2);
+  return true;
+}
+
+template <class T, int OI, int OO> struct Adv5State {
+  YWin<T, OI> yin;
+  YWin<T, OO> you;
+  T Fy_prev, fys_prev;  // yfx*fy2 / (fy+fy2)*mfy at the previous y-face
+  T fy2_c;              // inner y flux of the current row step (crosses its barriers)
+  const T* qg;          // this thread's (clamped) column of q, row -2
+  T* qo;
+  T* smt;               // this thread's slot of exchange row 0
+  T* qys;               // this thread's private slots (A5_GW apart): 0,1 qy by row parity; 2..5 inner x flux of the last four
+                        // rows; 6,7 / 8,9 tile-edge values of the inner / outer y stream
+};
+
+// per-thread view of the staged box of the current block of four row steps
+template <class T> struct A5View {
+  const Pair<T>* sp;
+  const T* ss;
+};
+#define A5P(v, f, k) ((v).sp[((f) * A5_R + (k)) * A5_GW])
+#define A5S(v, f, k) ((v).ss[((f) * A5_R + (k)) * A5_GW])
+#define A5XROW(s, k) ((s).smt + (k) * A5_XP)
+
+template <class T> FV3T_HD A5View<T> a5_view(const void* stage, int gtid) {
+  A5View<T> v;
+  v.sp = reinterpret_cast<const Pair<T>*>(stage) + gtid;
+  v.ss = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(stage) + A5Stage<T>::PAIR_BYTES) + gtid;
+  return v;
+}
+
+FV3T_HD Adv3Thr adv5_thread(const Adv5Cta& c, int tid) {
+  Adv3Thr t;
+  const int n = c.n;
+  t.tid = tid;
+  t.i = c.gb + tid;
+  const int ic = t.i > n + 3 ? n + 3 : t.i;
+  t.pix = ic + 2;
+  t.imx = t.imy = 0;
+  t.cell = (tid >= 3 && tid < c.nw + 3) ? 1 : 0;
+  t.icor = (t.i < 1 || t.i > n) ? 1 : 0;
+  keep(t.i);
+  keep(t.pix);
+  keep(t.cell);
+  keep(t.icor);
+  return t;
+}
+
+template <class T, int OI, int OO>
+FV3T_HD void adv5_init(const Adv5Params<T>& p, const Adv5Cta& c, const Adv3Thr& t, T* group_smem, Adv5State<T, OI, OO>& s) {
+  s.yin.init();
+  s.you.init();
+  s.Fy_prev = s.fys_prev = s.fy2_c = T(0);
+  s.qg = p.qin + c.qoff + t.pix;
+  s.qo = p.qout + c.qoff + t.pix;
+  keep_ptr(s.qg);
+  keep_ptr(s.qo);
+  s.smt = group_smem + A5_XPAD + t.tid;
+  s.qys = group_smem + A5_XROWS * A5_XP + t.tid;
+  for (int k = 0; k < A5Stage<T>::PRIV; ++k) s.qys[k * A5_GW] = T(0);
+}
+
+// asynchronous copy of q(i, r) into exchange row d; CORNER: rows outside 1..n also fetch the dir = 2 view into the private slot
+// (the x sweeps see the dir = 1 corner view of q, the y sweeps the dir = 2 view: copy_corners, tp_core.F90:265-328)
+template <class T, int OI, int OO, bool CORNER>
+FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r, int d) {
+  const int n = c.n, nd = c.nd, npx = c.npx;
+  if (!CORNER) {
+    async_copy<sizeof(T)>(A5XROW(s, d), s.qg + (r + 2) * nd);
+  } else {
+    r = r > n + 3 ? n + 3 : r;
+    const int i = t.i;
+    int ox = (r + 2) * nd, oy = ox;
+    if (t.icor && (r < 1 || r > n) && i <= n + 3) {
+      int s1i, s1j, s2i, s2j;
+      if (i < 1 && r < 1) {  // SW
+        s1i = r, s1j = 1 - i, s2i = 1 - r, s2j = i;
+      } else if (i > n && r < 1) {  // SE
+        s1i = npx - r, s1j = i - npx + 1, s2i = npx + r - 1, s2j = npx - i;
+      } else if (i > n) {  // NE
+        s1i = r, s1j = 2 * npx - 1 - i, s2i = 2 * npx - 1 - r, s2j = i;
+      } else {  // NW
+        s1i = npx - r, s1j = i - 1 + npx, s2i = r + 1 - npx, s2j = npx - i;
+      }
+      ox = (s1j + 2) * nd + (s1i - i);
+      oy = (s2j + 2) * nd + (s2i - i);
+    }
+    async_copy<sizeof(T)>(A5XROW(s, d), s.qg + ox);
+    if (r < 1 || r > n) async_copy<sizeof(T)>(s.qys + d * A5_GW, s.qg + oy);
+  }
+  async_commit();
+}
+
+// phase 1: inner y sweep (flux at y-face c = r-2), q_i of row o = r-3 to shared memory
+template <class T, int OI, int OO, int PH, bool YE>
+FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
+  constexpr int d = PH & 1;
+  const int nd = c.nd;
+  const int cc = r - 2;
+  const Pair<T> y2 = A5P(v, A5_Y2, PH);  // zero outside the faces 1..n+1 (k_prep5, TMA zero fill)
+  const T* dya = p.dya + c.tileoff + t.pix;
+  auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
+  T qy = A5XROW(s, d)[0];
+  if (YE && (r < 1 || r > c.n)) qy = s.qys[d * A5_GW];
+  const T q_o = s.yin.template q_cm1<PH>();
+  const T fy2_c = s.yin.template push<PH, YE>(cc, qy, y2.a, c.npx, p.lim_fac, met_y, s.qys + 6 * A5_GW, A5_GW);
+  const T Fy_c = y2.b * fy2_c;
+  const T qi = (q_o * A5S(v, A5_AO, PH) + s.Fy_prev - Fy_c) * A5S(v, A5_RY, PH);  // only rows o = 1..n are consumed
+  s.Fy_prev = Fy_c;
+  s.fy2_c = fy2_c;
+  A5XROW(s, 3)[0] = qi;
+}
+
+// phase 2: dm (ORD >= 7) or al (ORD < 7) of row r (inner x sweep) and of row o (outer x sweep on q_i)
+template <class T, int OI, int OO, int PH, bool XE>
+FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+  constexpr int d = PH & 1;
+  const int nd = c.nd;
+  const int rr = XE ? clampi(r, -2, c.n + 3) : r;
+  const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
+  const int i = t.i;
+  const T* dxa = p.dxa + c.tileoff + 2;
+  auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
+  auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
+  const T* sqa = A5XROW(s, d) - i;  // indexable by the global column
+  const T* sqb = A5XROW(s, 3) - i;
+  auto qa = [&](int gi) -> T { return sqa[gi]; };
+  auto qb = [&](int gi) -> T { return sqb[gi]; };
+  A5XROW(s, 2)[0] = ppm_pre<T, OI, XE>(i, c.npx, qa, dxa_r);
+  A5XROW(s, 4)[0] = ppm_pre<T, OO, XE>(i, c.npx, qb, dxa_o);
+}
+
+// phase 3: x-face fluxes: inner sweep of row r (-> xfx*fx2), outer sweep of row o (-> (fx+fx2)*mfx)
+template <class T, int OI, int OO, int PH, bool XE>
+FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
+  constexpr int d = PH & 1;
+  const int nd = c.nd;
+  const int rr = XE ? clampi(r, -2, c.n + 3) : r;
+  const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
+  const int i = t.i;
+  const T* dxa = p.dxa + c.tileoff + 2;
+  auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
+  auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
+  const T *sqa = A5XROW(s, d) - i, *sda = A5XROW(s, 2) - i, *sqb = A5XROW(s, 3) - i, *sdb = A5XROW(s, 4) - i;
+  auto qa = [&](int gi) -> T { return sqa[gi]; };
+  auto aa = [&](int gi) -> T { return sda[gi]; };
+  auto qb = [&](int gi) -> T { return sqb[gi]; };
+  auto ab = [&](int gi) -> T { return sdb[gi]; };
+  const Pair<T> x2r = A5P(v, A5_XR, PH);
+  const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, c.npx, p.lim_fac, qa, aa, dxa_r);
+  A5XROW(s, 5)[0] = x2r.b * fx2;
+  const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, c.npx, p.lim_fac, qb, ab, dxa_o);
+  A5XROW(s, 6)[0] = (fxo + s.qys[(2 + ((PH + 1) & 3)) * A5_GW]) * A5S(v, A5_MFX, PH);  // fx2 of row r-3, stored three row steps ago
+  s.qys[(2 + (PH & 3)) * A5_GW] = fx2;
+}
+
+// phase 4: q_j of row r, outer y sweep (flux at y-face c), flux-form update of row o
+template <class T, int OI, int OO, int PH, bool YE>
+FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
+  constexpr int d = PH & 1;
+  const int n = c.n, nd = c.nd;
+  const int cc = r - 2, o = r - 3;
+  const T* dya = p.dya + c.tileoff + t.pix;
+  auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
+  const T* sf1 = A5XROW(s, 5);
+  const T* sft = A5XROW(s, 6);
+  const T qx = A5XROW(s, d)[0];
+  const T q_o = s.yin.template q_cm1<PH>();  // the inner stream keeps q(c-1) = q(o) in slot PH+1 until the next push
+  const T qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) * A5S(v, A5_RX, PH);
+  const T fyo_c = s.you.template push<PH, YE>(cc, qj, A5P(v, A5_Y2, PH).a, c.npx, p.lim_fac, met_y, s.qys + 8 * A5_GW, A5_GW);
+  const T fys_c = (fyo_c + s.fy2_c) * A5S(v, A5_MFY, PH);  // mfy is zero outside the faces 1..n+1
+  const Pair<T> ab = A5P(v, A5_CAB, PH);
+  const T qnew = q_o * ab.a + (sft[0] - sft[1] + s.fys_prev - fys_c) * ab.b;
+  const bool o_ok = !YE || (o >= 1 && o <= n);
+  if (o_ok && t.cell) s.qo[(o + 2) * nd] = qnew;
+  s.fys_prev = fys_c;
+}
+
+// host restatement of what the producer warp's TMA boxes deliver for block b of (strip, level): test infrastructure
+// (tests/hostsim) and documentation of the box coordinates in one place
+template <class T> FV3T_HD void a5_box_rows(int b, int* row_of /*[A5_NPAIR + A5_NSC]*/) {
+  const int r0 = -2 + A5_R * b;  // first row step of the block; plane row = Fortran row + 2
+  row_of[A5_XR] = r0 + 2;        // row r
+  row_of[A5_XO] = r0 - 1;        // row o = r-3
+  row_of[A5_Y2] = r0;            // row c = r-2
+  row_of[A5_CAB] = r0 - 1;
+  row_of[A5_NPAIR + A5_RX] = r0 + 2;
+  row_of[A5_NPAIR + A5_MFX] = r0 - 1;
+  row_of[A5_NPAIR + A5_RY] = r0 - 1;
+  row_of[A5_NPAIR + A5_MFY] = r0;
+  row_of[A5_NPAIR + A5_AR] = r0 + 2;
+  row_of[A5_NPAIR + A5_AO] = r0 - 1;
+}
+
+#ifdef __CUDACC__
+// ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) ------------------------------------------------------------------
+__device__ __forceinline__ unsigned a5_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void a5_mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a5_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void a5_mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a5_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void a5_mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a5_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void a5_mbar_wait(uint64_t* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "A5_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra A5_DONE_%=;\n"
+      "bra A5_WAIT_%=;\n"
+      "A5_DONE_%=:\n"
+      "}\n" ::"r"(a5_smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void a5_tma_3d(void* dst, const CUtensorMap* m, int x, int y, int z, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   a5_smem_u32(dst)),
+               "l"(m), "r"(a5_smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void a5_group_sync(int g) {  // named barrier of one tracer group (ids 1..A5_MAXTG; 0 is __syncthreads)
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(A5_GW) : "memory");
+}
+
+// four row steps of one block
+template <class T, int OI, int OO, int PH, bool YE, bool XE>
+__device__ __forceinline__ void adv5_step(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
+                                          const A5View<T>& v, int r, int g) {
+  async_wait_all();                                              // q of row r (requested one row step ago) has landed
+  adv5_issue_q<T, OI, OO, YE>(c, s, t, r + 1, (PH & 1) ^ 1);     // request q of row r+1
+  adv5_phase1<T, OI, OO, PH, YE>(p, c, s, t, v, r);
+  a5_group_sync(g);
+  adv5_phase2<T, OI, OO, PH, XE>(p, c, s, t, r);
+  a5_group_sync(g);
+  adv5_phase3<T, OI, OO, PH, XE>(p, c, s, t, v, r);
+  a5_group_sync(g);
+  adv5_phase4<T, OI, OO, PH, YE>(p, c, s, t, v, r);
+}
+template <class T, int OI, int OO, bool YE, bool XE>
+__device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
+                                           const A5View<T>& v, int r0, int g) {
+  adv5_step<T, OI, OO, 0, YE, XE>(p, c, s, t, v, r0, g);
+  adv5_step<T, OI, OO, 1, YE, XE>(p, c, s, t, v, r0 + 1, g);
+  adv5_step<T, OI, OO, 2, YE, XE>(p, c, s, t, v, r0 + 2, g);
+  adv5_step<T, OI, OO, 3, YE, XE>(p, c, s, t, v, r0 + 3, g);
+}
+
+template <class T, int OI, int OO, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ Adv5Params<T> p, const __grid_constant__ Adv5Maps maps) {
+  extern __shared__ __align__(128) unsigned char smem5[];
+  using S = A5Stage<T>;
+  const int strip = blockIdx.x, levc = blockIdx.y;
+  const int n = p.n;
+  const int lev = p.lev0 + levc;
+  if (p.it > p.ksplt[lev % p.npz]) return;
+  const int iq_first = p.iq0 + blockIdx.z * p.tg;
+  const int tg = min(p.tg, p.iq0 + p.nql - iq_first);  // tracers of this CTA
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem5 + S::BAR_OFF);
+  uint64_t* empty = full + A5_NS;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < A5_NS; ++k) {
+      a5_mbar_init(&full[k], 1);
+      a5_mbar_init(&empty[k], 2 * tg);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int nblocks = (n + 6 + A5_R - 1) / A5_R;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    // ---- producer: one thread streams the level fields of the strip through the ring
+    if (threadIdx.x == 0) {
+      const int xs = strip * A5_W;  // plane column of group thread 0
+      const int tile = lev / p.npz;
+      int st = 0, wrap = 0;
+      for (int b = 0; b < nblocks; ++b) {
+        if (b >= A5_NS) a5_mbar_wait(&empty[st], (wrap - 1) & 1);
+        a5_mbar_expect_tx(&full[st], S::BYTES);
+        unsigned char* base = smem5 + st * S::BYTES;
+        constexpr int PB = A5_R * A5_GW * 2 * (int)sizeof(T), SB = A5_R * A5_GW * (int)sizeof(T);
+        const int r0 = -2 + A5_R * b;
+        a5_tma_3d(base + A5_XR * PB, &maps.x2, 2 * xs, r0 + 2, levc, &full[st]);
+        a5_tma_3d(base + A5_XO * PB, &maps.x2, 2 * xs, r0 - 1, levc, &full[st]);
+        a5_tma_3d(base + A5_Y2 * PB, &maps.y2, 2 * xs, r0, levc, &full[st]);
+        a5_tma_3d(base + A5_CAB * PB, &maps.cab, 2 * xs, r0 - 1, levc, &full[st]);
+        unsigned char* sb = base + S::PAIR_BYTES;
+        a5_tma_3d(sb + A5_RX * SB, &maps.rx, xs, r0 + 2, levc, &full[st]);
+        a5_tma_3d(sb + A5_MFX * SB, &maps.mfx, xs, r0 - 1, levc, &full[st]);
+        a5_tma_3d(sb + A5_RY * SB, &maps.ry, xs, r0 - 1, levc, &full[st]);
+        a5_tma_3d(sb + A5_MFY * SB, &maps.mfy, xs, r0, levc, &full[st]);
+        a5_tma_3d(sb + A5_AR * SB, &maps.area, xs, r0 + 2, tile, &full[st]);
+        a5_tma_3d(sb + A5_AO * SB, &maps.area, xs, r0 - 1, tile, &full[st]);
+        if (++st == A5_NS) {
+          st = 0;
+          ++wrap;
+        }
+      }
+    }
+    return;
+  }
+  // ---- consumers: group g marches tracer iq_first + g
+  const int ct = threadIdx.x - 32;
+  const int g = ct >> 6, gtid = ct & (A5_GW - 1);
+  if (g >= tg) return;
+  Adv5Cta c;
+  adv5_make_cta<T>(p, strip, levc, iq_first + g, c);
+  const Adv3Thr t = adv5_thread(c, gtid);
+  Adv5State<T, OI, OO> s;
+  T* gsm = reinterpret_cast<T*>(smem5 + S::GROUP_OFF) + (size_t)g * S::GROUP_ELEMS;
+  adv5_init<T, OI, OO>(p, c, t, gsm, s);
+  adv5_issue_q<T, OI, OO, true>(c, s, t, -2, 0);
+  int st = 0, wrap = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    const int r0 = -2 + A5_R * b;
+    a5_mbar_wait(&full[st], wrap & 1);
+    const A5View<T> v = a5_view<T>(smem5 + st * S::BYTES, gtid);
+    const bool yint = r0 >= 5 && r0 + 4 <= n;  // cells c = r-2 of the block are interior (3..npx-3) and rows r+1 <= n
+    if (yint) {
+      if (c.xedge)
+        adv5_block<T, OI, OO, false, true>(p, c, s, t, v, r0, g);
+      else
+        adv5_block<T, OI, OO, false, false>(p, c, s, t, v, r0, g);
+    } else {
+      adv5_block<T, OI, OO, true, true>(p, c, s, t, v, r0, g);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) a5_mbar_arrive(&empty[st]);
+    if (++st == A5_NS) {
+      st = 0;
+      ++wrap;
+    }
+  }
+  async_wait_all();
+}
+#endif
+
+}  // namespace fv3t

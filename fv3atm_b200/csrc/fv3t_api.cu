@@ -131,6 +131,14 @@ template <class T> struct Impl {
   // fast mode (fv3t_advect3.cuh): tracer-independent per-level scratch in plane layout, allocated on first use
   fv3t::Pair<T>*X2 = nullptr, *Y2 = nullptr, *cab = nullptr;
   T *rrx = nullptr, *rry = nullptr;
+  // multi-tracer TMA-staged advection (fv3t_advect5.cuh): padded-pitch scratch planes + their tensor maps
+  fv3t::Pair<T>*X5 = nullptr, *Y5 = nullptr, *C5 = nullptr;
+  T *RX5 = nullptr, *RY5 = nullptr, *MX5 = nullptr, *MY5 = nullptr, *AREA5 = nullptr;
+  fv3t::Adv5Maps maps5;
+  bool maps5_ok = false;
+  bool use5 = true;            // FV3T_ADV5=0 keeps the per-tracer k_advect4
+  bool call5 = false;          // the current tracer_2d call runs k_advect5
+  bool scale_pending = false;  // k_advect5 path: the in-place 1/ksplt scaling of cx, cy, mfx, mfy is applied by finish()
   fv3t::Pair<T>* P1 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
   T *GAM = nullptr, *RD1 = nullptr, *R2 = nullptr;
   cudaStream_t side = nullptr;            // remap_prepare: the coefficient kernel runs here, concurrently with tracer_2d
@@ -221,7 +229,8 @@ template <class T> struct Impl {
   int halo_local(int it);
   int halo_pack(int it, int lt, int edge, T* buf, bool unpack);
   int substep(int it, int hord, T lim_fac);
-  int prepare(int hord);
+  int prepare(int hord, bool allow5 = true);
+  int alloc5();
   int finish();
   int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
   int remap_resident(int nq, const int* kord, int fill, int j_first, int j_count);
@@ -272,6 +281,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   CK(dalloc(&cy, sz_cx() * nt));
   CK(dalloc(&pe, sz_pe() * nt));
   fast = !(getenv("FV3T_STRICT") && atoi(getenv("FV3T_STRICT")) != 0);
+  use5 = !(getenv("FV3T_ADV5") && atoi(getenv("FV3T_ADV5")) == 0);
   CK(cudaMemsetAsync(q[0], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(q[1], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(delp, 0, sz_c() * nt * sizeof(T), stream));
@@ -346,7 +356,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -510,10 +520,58 @@ template <class T, int OI, int OO> int launch_advect(Impl<T>& c, fv3t::Adv2Param
 
 // steps A and C of tracer_2d: xfx, yfx and the in-place 1/ksplt scaling of cx, cy, mfx, mfy (fv_tracer2d.F90:387-405,
 // 449-486); the fast path additionally prepares 1/ra_x, 1/ra_y and the dp1/dp2 factors (fv3t_advect3.cuh, k_prep3)
-template <class T> int Impl<T>::prepare(int hord) {
+template <class T> int Impl<T>::alloc5() {
+  if (maps5_ok) return 0;
+  const int nd = n + 6, PP = fv3t::a5_pitch(n);
+  const size_t e = (size_t)nt * npz * nd * PP;
+  auto zalloc = [&](void** p, size_t bytes) -> cudaError_t {
+    if (*p) return cudaSuccess;
+    cudaError_t r = cudaMalloc(p, bytes);
+    if (r != cudaSuccess) return r;
+    return cudaMemsetAsync(*p, 0, bytes, stream);  // the padding columns and the cells outside the valid faces stay zero
+  };
+  CK(zalloc((void**)&X5, e * sizeof(fv3t::Pair<T>)));
+  CK(zalloc((void**)&Y5, e * sizeof(fv3t::Pair<T>)));
+  CK(zalloc((void**)&C5, e * sizeof(fv3t::Pair<T>)));
+  CK(zalloc((void**)&RX5, e * sizeof(T)));
+  CK(zalloc((void**)&RY5, e * sizeof(T)));
+  CK(zalloc((void**)&MX5, e * sizeof(T)));
+  CK(zalloc((void**)&MY5, e * sizeof(T)));
+  CK(zalloc((void**)&AREA5, (size_t)nt * nd * PP * sizeof(T)));
+  CK(fv3t::fast_pad_plane<T>(AREA5, area, nd, PP, nt, stream));
+  ++launches;
+  fv3t::Adv5Params<T> p{};
+  p.X2 = X5;
+  p.Y2 = Y5;
+  p.CAB = C5;
+  p.RX = RX5;
+  p.RY = RY5;
+  p.MFX = MX5;
+  p.MFY = MY5;
+  p.AREA = AREA5;
+  p.n = n;
+  p.npz = npz;
+  p.ntiles = nt;
+  const cudaError_t r = fv3t::fast_advect5_maps<T>(&maps5, p, nt * npz);
+  if (r != cudaSuccess) return fail("fv3tracer: cuTensorMapEncodeTiled failed (%s)", cudaGetErrorString(r));
+  maps5_ok = true;
+  return 0;
+}
+
+template <class T> int Impl<T>::prepare(int hord, bool allow5) {
   call_fast = fast && fv3t::fast_hord_ok(hord);
+  call5 = call_fast && use5 && allow5 && fv3t::adv5_hord_ok(hord);
   auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
-  if (call_fast) {
+  if (call5) {
+    const int rc = alloc5();
+    if (rc) return rc;
+    fv3t::Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X5, Y5, C5, RX5, RY5, MX5, MY5,
+                            ksplt_d, n, npz, nt, 0, nt * npz, 1, 1};
+    kbegin();
+    CK(fv3t::fast_prep5<T>(pp, stream));
+    kend(KC_SCALE);
+    scale_pending = nsplt != 1;
+  } else if (call_fast) {
     const size_t e = sz_c() * nt;
     CK(dalloc((void**)&X2, e * sizeof(fv3t::Pair<T>)));
     CK(dalloc((void**)&Y2, e * sizeof(fv3t::Pair<T>)));
@@ -550,6 +608,47 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   if (!prep_done) {
     const int rc = prepare(hord);
     if (rc) return rc;
+  }
+  if (call5) {
+    if (!fv3t::adv5_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
+    if (it > 1) {  // dp1 <- dp2 of sub-step it-1 (fv_tracer2d.F90:547-553), then dp1/dp2, 0.5*rarea/dp2 of this sub-step
+      fv3t::Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X5, Y5, C5, RX5, RY5, MX5, MY5,
+                              ksplt_d, n, npz, nt, 0, nt * npz, it, 0};
+      kbegin();
+      CK(fv3t::fast_prep5<T>(pp, stream));
+      kend(KC_SCALE);
+    }
+    fv3t::Adv5Params<T> p{};
+    p.qin = q[(cur + it - 1) & 1];
+    p.qout = q[(cur + it) & 1];
+    p.X2 = X5;
+    p.Y2 = Y5;
+    p.CAB = C5;
+    p.RX = RX5;
+    p.RY = RY5;
+    p.MFX = MX5;
+    p.MFY = MY5;
+    p.AREA = AREA5;
+    p.dxa = dxa;
+    p.dya = dya;
+    p.ksplt = ksplt_d;
+    p.n = n;
+    p.npz = npz;
+    p.nq = nq_cur;
+    p.ntiles = nt;
+    p.it = it;
+    p.lev0 = 0;
+    p.iq0 = 0;
+    p.nql = nq_cur;
+    p.lim_fac = lim_fac;
+    if (coef_wanted && it == 1 && !prof) {
+      const int rcs = launch_coef_side();
+      if (rcs) return rcs;
+    }
+    kbegin();
+    CK(fv3t::fast_advect5<T>(p, maps5, hord, nt * npz, stream));
+    kend(KC_ADVECT);
+    return 0;
   }
   if (call_fast) {
     if (!fv3t::fast_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
@@ -644,6 +743,12 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
 
 template <class T> int Impl<T>::finish() {
   CK(cudaSetDevice(device));
+  if (scale_pending) {  // the post-state the caller sees (fv_tracer2d.F90:463-481); k_prep5 read the unscaled arrays
+    kbegin();
+    CK(fv3t::fast_scale3<T>(cx, cy, mfx, mfy, ksplt_d, n, npz, nt, stream));
+    kend(KC_SCALE);
+    scale_pending = false;
+  }
   // level k has been advanced ksplt(k) times and lives in q[(cur + ksplt(k)) & 1]; gather every level in q[(cur + nsplt) & 1]
   const int fin = (cur + nsplt) & 1;
   if (nsplt != 1) {
@@ -872,7 +977,7 @@ int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const
     ev_done.push_back(b);
   }
   nq_cur = nq;
-  if ((rc = prepare(hord))) return rc;  // k_prep3 (nsplt == 1: nothing is scaled in place)
+  if ((rc = prepare(hord, false))) return rc;  // k_prep3 (nsplt == 1: nothing is scaled in place); per-tracer launches: k_advect4
   if ((rc = remap_alloc())) return rc;
   const int c0 = cur;                   // per tracer: advect q[c0] -> q[c0^1], remap q[c0^1] -> q[c0]
   fv3t::Remap3Params<T> rp{q[c0 ^ 1], q[c0], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, nq, nt, fill};

@@ -26,6 +26,15 @@ template <class T> FV3T_HD T f_min(T a, T b, T c) { return f_min(f_min(a, b), c)
 template <class T> FV3T_HD T f_max(T a, T b, T c, T d) { return f_max(f_max(f_max(a, b), c), d); }
 template <class T> FV3T_HD T f_min(T a, T b, T c, T d) { return f_min(f_min(f_min(a, b), c), d); }
 
+// sign(min(|x|, |y|), x) (tp_core.F90:575-576) without materialising the absolute values: the magnitude comes from whichever
+// operand is smaller in modulus, the sign bit is overwritten anyway.  Bit-identical to f_sign(f_min(f_abs(x), f_abs(y)), x).
+template <class T> FV3T_HD T sign_min_abs(T x, T y) { return f_sign((f_abs(x) < f_abs(y)) ? x : y, x); }
+// sign(min(|xt|, max(m, 0)), xt) (the monotone slope of tp_core.F90:563-567 once m = min(hi - q0, q0 - lo) is known), same idea
+template <class T> FV3T_HD T dm_limit(T xt, T m) {
+  const T t = (f_abs(xt) < m) ? xt : m;
+  return f_sign((m > T(0)) ? t : T(0), xt);
+}
+
 // L1 prefetch of a global line that a later iteration of a column sweep will read (no register is tied up)
 FV3T_HD void prefetch_l1(const void* p) {
 #ifdef __CUDA_ARCH__

@@ -2,6 +2,7 @@
 #include "fv3t_fast.h"
 
 #include <cstdlib>
+#include <cudaTypedefs.h>
 
 namespace fv3t {
 
@@ -71,6 +72,90 @@ template <class T> cudaError_t fast_advect3(Adv3Params<T> p, int hord, int NT, c
   }
 }
 
+
+// ---- k_advect5 -------------------------------------------------------------------------------------------------------------
+template <class T> cudaError_t fast_prep5(const Prep5Params<T>& p, cudaStream_t stream) {
+  dim3 grid(32, p.nlev);
+  k_prep5<T><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+template <class T> cudaError_t fast_pad_plane(T* dst, const T* src, int nd, int PP, int ntiles, cudaStream_t stream) {
+  k_pad_plane<T><<<296, 256, 0, stream>>>(dst, src, nd, PP, ntiles);
+  return cudaGetLastError();
+}
+
+typedef CUresult (*fv3t_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static fv3t_encode_fn tensor_map_encoder() {
+  static fv3t_encode_fn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (fv3t_encode_fn)f;
+  }
+  return fn;
+}
+// [planes][nd rows][PP * per columns] of T, box = (A5_GW * per) x A5_R x 1, out-of-bounds elements read as zero
+template <class T> static cudaError_t encode_plane_map(CUtensorMap* m, const void* base, int PP, int nd, int planes, int per) {
+  fv3t_encode_fn enc = tensor_map_encoder();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t gdim[3] = {(cuuint64_t)PP * per, (cuuint64_t)nd, (cuuint64_t)planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)PP * per * sizeof(T), (cuuint64_t)PP * per * sizeof(T) * nd};
+  const cuuint32_t box[3] = {(cuuint32_t)(A5_GW * per), (cuuint32_t)A5_R, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T>& p, int nlev) {
+  const int nd = p.n + 6, PP = a5_pitch(p.n);
+  cudaError_t e;
+  if ((e = encode_plane_map<T>(&m->x2, p.X2, PP, nd, nlev, 2)) != cudaSuccess) return e;
+  if ((e = encode_plane_map<T>(&m->y2, p.Y2, PP, nd, nlev, 2)) != cudaSuccess) return e;
+  if ((e = encode_plane_map<T>(&m->cab, p.CAB, PP, nd, nlev, 2)) != cudaSuccess) return e;
+  if ((e = encode_plane_map<T>(&m->rx, p.RX, PP, nd, nlev, 1)) != cudaSuccess) return e;
+  if ((e = encode_plane_map<T>(&m->ry, p.RY, PP, nd, nlev, 1)) != cudaSuccess) return e;
+  if ((e = encode_plane_map<T>(&m->mfx, p.MFX, PP, nd, nlev, 1)) != cudaSuccess) return e;
+  if ((e = encode_plane_map<T>(&m->mfy, p.MFY, PP, nd, nlev, 1)) != cudaSuccess) return e;
+  return encode_plane_map<T>(&m->area, p.AREA, PP, nd, p.ntiles, 1);
+}
+
+template <class T, int OI, int OO, int TGC> static cudaError_t launch5(const Adv5Params<T>& p, const Adv5Maps& m, dim3 grid, cudaStream_t stream) {
+  constexpr int NTHR = 32 + A5_GW * TGC;
+  constexpr int MINB = 1;  // the named barriers of the tracer groups take all 16 hardware barriers: one CTA per SM
+  const size_t smem = A5Stage<T>::smem_bytes(p.tg);
+  cudaError_t e = cudaFuncSetAttribute(k_advect5<T, OI, OO, NTHR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_advect5<T, OI, OO, NTHR, MINB><<<grid, 32 + A5_GW * p.tg, smem, stream>>>(p, m);
+  return cudaGetLastError();
+}
+template <class T, int OI, int OO> static cudaError_t launch5_ord(Adv5Params<T>& p, const Adv5Maps& m, int nlev, cudaStream_t stream) {
+  // tracers per CTA: every tracer group of a CTA shares the staged level fields.  FV3T_ADV_TG caps it (tuning knob).
+  static const int cap_env = getenv("FV3T_ADV_TG") ? atoi(getenv("FV3T_ADV_TG")) : A5_MAXTG;
+  const int cap = cap_env < 1 ? 1 : (cap_env > A5_MAXTG ? A5_MAXTG : cap_env);
+  const int chunks = (p.nql + cap - 1) / cap;
+  p.tg = (p.nql + chunks - 1) / chunks;
+  const int strips = (p.n + A5_W - 1) / A5_W;
+  dim3 grid(strips, nlev, chunks);
+  if (p.tg > 5) return launch5<T, OI, OO, 9>(p, m, grid, stream);
+  return launch5<T, OI, OO, 5>(p, m, grid, stream);
+}
+template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+  switch (hord) {
+    case 8: return launch5_ord<T, 8, 8>(p, m, nlev, stream);
+    case 10: return launch5_ord<T, 8, 10>(p, m, nlev, stream);
+#ifndef FV3T_A5_DEV
+    case 9: return launch5_ord<T, 9, 9>(p, m, nlev, stream);
+    case 11: return launch5_ord<T, 11, 11>(p, m, nlev, stream);
+    case 12: return launch5_ord<T, 12, 12>(p, m, nlev, stream);
+    case 13: return launch5_ord<T, 13, 13>(p, m, nlev, stream);
+    case 2: return launch5_ord<T, 2, 2>(p, m, nlev, stream);
+#endif
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaStream_t stream) {
   dim3 grid((p.n * p.n + 127) / 128, p.ntiles);
   k_remap_coef3<T><<<grid, 128, 0, stream>>>(p);
@@ -106,9 +191,17 @@ template <class T> cudaError_t fast_remap3(const Remap3Params<T>& p, int akord, 
   template cudaError_t fast_scale3<T>(T*, T*, T*, T*, const int*, int, int, int, cudaStream_t);                       \
   template cudaError_t fast_cab3<T>(const Cab3Params<T>&, int, cudaStream_t);                                         \
   template cudaError_t fast_advect3<T>(Adv3Params<T>, int, int, cudaStream_t);                                        \
+  template cudaError_t fast_prep5<T>(const Prep5Params<T>&, cudaStream_t);                                            \
+  template cudaError_t fast_pad_plane<T>(T*, const T*, int, int, int, cudaStream_t);                                  \
+  template cudaError_t fast_advect5_maps<T>(Adv5Maps*, const Adv5Params<T>&, int);                                    \
+  template cudaError_t fast_advect5<T>(Adv5Params<T>, const Adv5Maps&, int, int, cudaStream_t);                       \
   template cudaError_t fast_remap_coef3<T>(const Remap3Params<T>&, cudaStream_t);                                     \
   template cudaError_t fast_remap3<T>(const Remap3Params<T>&, int, cudaStream_t);
+#if defined(FV3T_INST_F64) || !defined(FV3T_INST_F32)
 FV3T_FAST_INST(double)
+#endif
+#if defined(FV3T_INST_F32) || !defined(FV3T_INST_F64)
 FV3T_FAST_INST(float)
+#endif
 
 }  // namespace fv3t

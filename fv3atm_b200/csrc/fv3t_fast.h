@@ -6,6 +6,7 @@
 
 #include "fv3t_advect3.cuh"
 #include "fv3t_advect4.cuh"
+#include "fv3t_advect5.cuh"
 #include "fv3t_remap3.cuh"
 
 namespace fv3t {
@@ -25,5 +26,16 @@ template <class T> cudaError_t fast_scale3(T* cx, T* cy, T* mfx, T* mfy, const i
 template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cudaStream_t stream);
 // NT = threads per CTA (strip width NT-6); p.W is set by the launcher
 template <class T> cudaError_t fast_advect3(Adv3Params<T> p, int hord, int NT, cudaStream_t stream);
+
+// ---- multi-tracer TMA-staged advection (fv3t_advect5.cuh) ----
+// schemes instantiated for k_advect5 (a subset of fast_hord_ok keeps the build time bounded)
+inline bool adv5_hord_ok(int hord) { return hord == 8 || hord == 10 || hord == 9 || hord == 12 || hord == 13 || hord == 11 || hord == 2; }
+template <class T> cudaError_t fast_prep5(const Prep5Params<T>& p, cudaStream_t stream);
+template <class T> cudaError_t fast_pad_plane(T* dst, const T* src, int nd, int PP, int ntiles, cudaStream_t stream);
+// tensor maps of the scratch planes (nlev levels resident) and of the padded area array; returns cudaErrorNotSupported
+// when the driver lacks cuTensorMapEncodeTiled
+template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T>& p, int nlev);
+// p.tg is chosen by the launcher; nlev = levels of the resident chunk (grid.y)
+template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
 
 }  // namespace fv3t

@@ -63,18 +63,19 @@ template <class T, class QF, class DF> FV3T_HD T edge_value(int e0, QF q, DF dxa
 }
 
 // phase "pre": dm(i) for ORD >= 7 (tp_core.F90:563-567), al(i) for ORD < 7 (:377-400)
-template <class T, int ORD, class QF, class DF> FV3T_HD T ppm_pre(int i, int npx, QF q, DF dxa) {
+template <class T, int ORD, bool EDGE = true, class QF, class DF> FV3T_HD T ppm_pre(int i, int npx, QF q, DF dxa) {
   if (ORD >= 7) {
     // = sign(min(|xt|, max(qm,q0,qp) - q0, q0 - min(qm,q0,qp)), xt), bit-identical, three comparisons (see dm_of)
     const T qm = q(i - 1), q0 = q(i), qp = q(i + 1);
     const T xt = T(0.25) * (qp - qm);
     const bool up = qm < qp;
     const T lo = up ? qm : qp, hi = up ? qp : qm;
-    const T m = f_max(f_min(hi - q0, q0 - lo), T(0));
-    return f_sign(f_min(f_abs(xt), m), xt);
+    return dm_limit<T>(xt, f_min(hi - q0, q0 - lo));
   } else {
     T al;
-    if (i == 0) {
+    if (!EDGE) {
+      al = K<T>::p1() * (q(i - 1) + q(i)) + K<T>::p2() * (q(i - 2) + q(i + 1));
+    } else if (i == 0) {
       al = K<T>::c1() * q(-2) + K<T>::c2() * q(-1) + K<T>::c3() * q(0);
     } else if (i == 1) {
       al = edge_value<T>(1, q, dxa);
@@ -95,7 +96,7 @@ template <class T, int ORD, class QF, class DF> FV3T_HD T ppm_pre(int i, int npx
 }
 
 // phase "blbr" for cell i.  `a` = dm (ORD >= 7) or al (ORD < 7).  flg: bit0 smt5, bit1 smt6 (ORD < 7 only).
-template <class T, int ORD, class QF, class AF, class DF>
+template <class T, int ORD, bool EDGE = true, class QF, class AF, class DF>
 FV3T_HD void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T lim_fac, T& bl, T& br, int& flg) {
   flg = 0;
   const T q0 = q(i);
@@ -134,7 +135,7 @@ FV3T_HD void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T lim_fac, T& bl, T& b
     return;
   }
   // ---- ORD >= 7 ----
-  if (i <= 2) {  // west / south tile edge, cells 0,1,2 (tp_core.F90:637-656)
+  if (EDGE && i <= 2) {  // west / south tile edge, cells 0,1,2 (tp_core.F90:637-656)
     T xt = edge_value<T>(1, q, dxa);
     xt = f_max(xt, f_min(q(-1), q(0), q(1), q(2)));
     xt = f_min(xt, f_max(q(-1), q(0), q(1), q(2)));
@@ -153,7 +154,7 @@ FV3T_HD void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T lim_fac, T& bl, T& b
     pert_ppm1<T>(q0, bl, br, 1);
     return;
   }
-  if (i >= npx - 2) {  // east / north tile edge, cells npx-2, npx-1, npx (tp_core.F90:657-674)
+  if (EDGE && i >= npx - 2) {  // east / north tile edge, cells npx-2, npx-1, npx (tp_core.F90:657-674)
     const T xt2 = K<T>::s15() * q(npx - 1) + K<T>::s11() * q(npx - 2) + K<T>::s14() * a(npx - 2);
     T xt = edge_value<T>(npx, q, dxa);
     xt = f_max(xt, f_min(q(npx - 2), q(npx - 1), q(npx), q(npx + 1)));
@@ -179,8 +180,8 @@ FV3T_HD void ppm_blbr(int i, int npx, QF q, AF a, DF dxa, T lim_fac, T& bl, T& b
   const T al1 = T(0.5) * (q0 + qp) + K<T>::r3() * (dm0 - a(i + 1));
   if (ORD == 8 || ORD == 11) {
     const T xt = (ORD == 8 ? T(2) : K<T>::ppm_fac()) * dm0;
-    bl = -f_sign(f_min(f_abs(xt), f_abs(al0 - q0)), xt);
-    br = f_sign(f_min(f_abs(xt), f_abs(al1 - q0)), xt);
+    bl = -sign_min_abs<T>(xt, al0 - q0);
+    br = sign_min_abs<T>(xt, al1 - q0);
   } else if (ORD == 10) {
     bl = al0 - q0;
     br = al1 - q0;

@@ -1,0 +1,202 @@
+// TEST INFRASTRUCTURE ONLY: runs the product's multi-tracer advection path (fv3atm_b200/csrc/fv3t_advect5.cuh: prep5_cell and the
+// four phase functions of a marching tracer group) on the CPU, one simulated thread after the other between barriers, with the
+// TMA boxes of the producer warp restated as plain copies (zero fill outside the tensor), so that the kernel logic can be
+// compared with the oracle where no GPU exists.  Not a fallback: nothing in fv3atm_b200/ links this.  Host orchestration
+// mirrors Impl<T>::substep / prepare of fv3t_api.cu (k_advect5 path).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../fv3atm_b200/csrc/fv3t_advect5.cuh"
+
+using namespace fv3t;
+
+// what the ten cp.async.bulk.tensor boxes of block b deliver (k_advect5, producer warp)
+template <class T> static void fill_stage(const Adv5Params<T>& p, int strip, int levc, int b, unsigned char* stage) {
+  const int n = p.n, nd = n + 6, PP = a5_pitch(n);
+  const int lev = p.lev0 + levc, tile = lev / p.npz;
+  const int xs = strip * A5_W;
+  int rows[A5_NPAIR + A5_NSC];
+  a5_box_rows<T>(b, rows);
+  const Pair<T>* psrc[A5_NPAIR] = {p.X2, p.X2, p.Y2, p.CAB};
+  Pair<T>* pd = reinterpret_cast<Pair<T>*>(stage);
+  for (int f = 0; f < A5_NPAIR; ++f)
+    for (int k = 0; k < A5_R; ++k)
+      for (int x = 0; x < A5_GW; ++x) {
+        const int row = rows[f] + k, col = xs + x;
+        Pair<T> v{T(0), T(0)};
+        if (row >= 0 && row < nd && col >= 0 && col < PP) v = psrc[f][((long)levc * nd + row) * PP + col];
+        pd[(f * A5_R + k) * A5_GW + x] = v;
+      }
+  const T* ssrc[A5_NSC] = {p.RX, p.MFX, p.RY, p.MFY, p.AREA, p.AREA};
+  T* sd = reinterpret_cast<T*>(stage + A5Stage<T>::PAIR_BYTES);
+  for (int f = 0; f < A5_NSC; ++f)
+    for (int k = 0; k < A5_R; ++k)
+      for (int x = 0; x < A5_GW; ++x) {
+        const int row = rows[A5_NPAIR + f] + k, col = xs + x;
+        const long plane_idx = (f >= A5_AR) ? tile : levc;
+        T v = T(0);
+        if (row >= 0 && row < nd && col >= 0 && col < PP) v = ssrc[f][(plane_idx * nd + row) * PP + col];
+        sd[(f * A5_R + k) * A5_GW + x] = v;
+      }
+}
+
+template <class T, int OI, int OO, int PH, bool YE, bool XE>
+static void sim_step(const Adv5Params<T>& p, const Adv5Cta& c, std::vector<Adv5State<T, OI, OO>>& st, const std::vector<Adv3Thr>& th,
+                     const unsigned char* stage, int r) {
+  const int NT = A5_GW;
+  for (int tid = 0; tid < NT; ++tid) {
+    adv5_issue_q<T, OI, OO, YE>(c, st[tid], th[tid], r + 1, (PH & 1) ^ 1);
+    adv5_phase1<T, OI, OO, PH, YE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
+  }
+  for (int tid = 0; tid < NT; ++tid) adv5_phase2<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], r);
+  for (int tid = 0; tid < NT; ++tid) adv5_phase3<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
+  for (int tid = 0; tid < NT; ++tid) adv5_phase4<T, OI, OO, PH, YE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
+}
+template <class T, int OI, int OO, bool YE, bool XE>
+static void sim_block(const Adv5Params<T>& p, const Adv5Cta& c, std::vector<Adv5State<T, OI, OO>>& st, const std::vector<Adv3Thr>& th,
+                      const unsigned char* stage, int r0) {
+  sim_step<T, OI, OO, 0, YE, XE>(p, c, st, th, stage, r0);
+  sim_step<T, OI, OO, 1, YE, XE>(p, c, st, th, stage, r0 + 1);
+  sim_step<T, OI, OO, 2, YE, XE>(p, c, st, th, stage, r0 + 2);
+  sim_step<T, OI, OO, 3, YE, XE>(p, c, st, th, stage, r0 + 3);
+}
+
+template <class T, int OI, int OO> static void run_substep(const Adv5Params<T>& p) {
+  const int n = p.n;
+  const int strips = (n + A5_W - 1) / A5_W;
+  const int nblocks = (n + 6 + A5_R - 1) / A5_R;
+  std::vector<unsigned char> stage(A5Stage<T>::BYTES + 16);
+  unsigned char* sg = stage.data() + ((16 - ((uintptr_t)stage.data() & 15)) & 15);
+  std::vector<T> gsm(A5Stage<T>::GROUP_ELEMS + 2);
+  T* gs = gsm.data() + (((uintptr_t)gsm.data() & 15) ? 1 : 0);
+  std::vector<Adv5State<T, OI, OO>> st(A5_GW);
+  std::vector<Adv3Thr> th(A5_GW);
+  for (int levc = 0; levc < p.ntiles * p.npz; ++levc)
+    for (int strip = 0; strip < strips; ++strip)
+      for (int iq = p.iq0; iq < p.iq0 + p.nql; ++iq) {
+        Adv5Cta c;
+        if (!adv5_make_cta<T>(p, strip, levc, iq, c)) continue;
+        for (int tid = 0; tid < A5_GW; ++tid) {
+          th[tid] = adv5_thread(c, tid);
+          adv5_init<T, OI, OO>(p, c, th[tid], gs, st[tid]);
+          adv5_issue_q<T, OI, OO, true>(c, st[tid], th[tid], -2, 0);
+        }
+        for (int b = 0; b < nblocks; ++b) {
+          const int r0 = -2 + A5_R * b;
+          fill_stage<T>(p, strip, levc, b, sg);
+          const bool yint = r0 >= 5 && r0 + 4 <= n;
+          if (yint) {
+            if (c.xedge)
+              sim_block<T, OI, OO, false, true>(p, c, st, th, sg, r0);
+            else
+              sim_block<T, OI, OO, false, false>(p, c, st, th, sg, r0);
+          } else {
+            sim_block<T, OI, OO, true, true>(p, c, st, th, sg, r0);
+          }
+        }
+      }
+}
+
+template <class T> static int dispatch(const Adv5Params<T>& p, int hord) {
+  switch (hord) {
+    case 8: run_substep<T, 8, 8>(p); break;
+    case 10: run_substep<T, 8, 10>(p); break;
+    case 9: run_substep<T, 9, 9>(p); break;
+    case 11: run_substep<T, 11, 11>(p); break;
+    case 12: run_substep<T, 12, 12>(p); break;
+    case 13: run_substep<T, 13, 13>(p); break;
+    case 2: run_substep<T, 2, 2>(p); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+// q [6, nq, npz, nd, nd] in/out; dp1 [6, npz, nd, nd] in/out; cx, cy, mfx, mfy in/out (scaled when nsplt != 1)
+template <class T>
+static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area, const T* rarea,
+                         const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, const int64_t* halo_dst,
+                         const int64_t* halo_src, int64_t halo_len, int hord, T lim_fac, int nsplt, const int* ksplt) {
+  const int nt = 6, nd = n + 6, PP = a5_pitch(n);
+  const long plane = (long)nd * nd;
+  const size_t nlev = (size_t)nt * npz, pe = nlev * nd * PP;
+  std::vector<Pair<T>> X2(pe, Pair<T>{T(0), T(0)}), Y2(pe, Pair<T>{T(0), T(0)}), CAB(pe, Pair<T>{T(0), T(0)});
+  std::vector<T> RX(pe, T(0)), RY(pe, T(0)), MX(pe, T(0)), MY(pe, T(0)), AREA((size_t)nt * nd * PP, T(0));
+  for (int t = 0; t < nt; ++t)
+    for (int r = 0; r < nd; ++r)
+      for (int x = 0; x < nd; ++x) AREA[((size_t)t * nd + r) * PP + x] = area[(size_t)t * plane + (size_t)r * nd + x];
+  std::vector<T> qb((size_t)nt * nq * npz * plane);
+  const long tile_stride = plane * npz * nq;
+  for (int it = 1; it <= nsplt; ++it) {
+    Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X2.data(), Y2.data(), CAB.data(), RX.data(),
+                      RY.data(), MX.data(), MY.data(), ksplt, n, npz, nt, 0, (int)nlev, it, it == 1 ? 1 : 0};
+    for (int levc = 0; levc < (int)nlev; ++levc)
+      for (int e = 0; e < (int)plane; ++e) prep5_cell<T>(pp, levc, e);
+    // edge-halo fill of every plane (complete_group_halo_update, fv_tracer2d.F90:499)
+    for (long pl = 0; pl < (long)nq * npz; ++pl)
+      for (int64_t e = 0; e < halo_len; ++e) {
+        const int64_t d = halo_dst[e], s = halo_src[e];
+        q[(d / plane) * tile_stride + pl * plane + d % plane] = q[(s / plane) * tile_stride + pl * plane + s % plane];
+      }
+    Adv5Params<T> p{};
+    p.qin = q;
+    p.qout = qb.data();
+    p.X2 = X2.data();
+    p.Y2 = Y2.data();
+    p.CAB = CAB.data();
+    p.RX = RX.data();
+    p.RY = RY.data();
+    p.MFX = MX.data();
+    p.MFY = MY.data();
+    p.AREA = AREA.data();
+    p.dxa = dxa;
+    p.dya = dya;
+    p.ksplt = ksplt;
+    p.n = n;
+    p.npz = npz;
+    p.nq = nq;
+    p.ntiles = nt;
+    p.it = it;
+    p.lev0 = 0;
+    p.tg = 1;
+    p.iq0 = 0;
+    p.nql = nq;
+    p.lim_fac = lim_fac;
+    if (dispatch<T>(p, hord)) return 1;
+    for (int t = 0; t < nt; ++t)
+      for (int iq = 0; iq < nq; ++iq)
+        for (int kz = 0; kz < npz; ++kz) {
+          if (it > ksplt[kz]) continue;
+          const long o = (((long)t * nq + iq) * npz + kz) * plane;
+          for (int j = 1; j <= n; ++j)
+            std::memcpy(q + o + (long)(j + 2) * nd + 3, qb.data() + o + (long)(j + 2) * nd + 3, sizeof(T) * n);
+        }
+  }
+  // the in-place 1/ksplt scaling of cx, cy, mfx, mfy (fv_tracer2d.F90:463-481) is applied last (Impl<T>::finish)
+  if (nsplt != 1) {
+    const long ncx = (long)(n + 1) * nd, nmf = (long)(n + 1) * n;
+    for (size_t lev = 0; lev < nlev; ++lev) {
+      const T frac = T(1) / (T)ksplt[lev % npz];
+      for (long e = 0; e < ncx; ++e) {
+        cx[lev * ncx + e] *= frac;
+        cy[lev * ncx + e] *= frac;
+      }
+      for (long e = 0; e < nmf; ++e) {
+        mfx[lev * nmf + e] *= frac;
+        mfy[lev * nmf + e] *= frac;
+      }
+    }
+  }
+  return 0;
+}
+
+#define API(T, S)                                                                                                              \
+  extern "C" int hostsim5_tracer_2d_##S(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area,     \
+                                        const T* rarea, const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, \
+                                        const int64_t* halo_dst, const int64_t* halo_src, int64_t halo_len, int hord,          \
+                                        T lim_fac, int nsplt, const int* ksplt) {                                              \
+    return tracer_2d_sim<T>(n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst, halo_src,  \
+                            halo_len, hord, lim_fac, nsplt, ksplt);                                                            \
+  }
+API(double, f64)
+API(float, f32)
