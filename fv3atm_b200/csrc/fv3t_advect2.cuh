@@ -272,6 +272,15 @@ FV3T_HD T ystream_core(int c, T qm2, T qm1, T q0, T qp1, T qp2, T a_m1, T a_0, T
     }
   }
   // flux at face c
+  if (ORD >= 8) {
+    // ppm_flux's single expression for both wind directions, with the upwind cell picked by three selects instead of index
+    // comparisons in accessor lambdas (which the compiler turned into ~15 predicated moves per face)
+    const bool up = cour > T(0);
+    const T a = f_abs(cour);
+    const T blu = up ? bl_m1 : bl, bru = up ? br_m1 : br, qu = up ? qm1 : q0;
+    const T b = up ? bru : blu;
+    return qu + (T(1) - a) * (b - a * (blu + bru));
+  }
   const T qm1_ = qm1, q0_ = q0, blm = bl_m1, brm = br_m1;
   const T bl_ = bl, br_ = br;
   const int flm = fl_m1, fl_ = fl;

@@ -28,7 +28,13 @@ constexpr int A5_GW = 64;  // threads (columns) per tracer group: 58 compute col
 constexpr int A5_W = A5_GW - 6;
 constexpr int A5_XP = A5_GW + 8;  // pitch of an exchange row (4 pad slots either side)
 constexpr int A5_XPAD = 4;
-constexpr int A5_XROWS = 7;  // 0,1 q of row r (by row parity)  2 dm/al of row r  3 q_i of row o  4 dm/al of row o  5 xfx*fx2  6 (fx+fx2)*mfx
+// exchange rows of a tracer group: 0..3 q of row r (slot = row step mod 4)  4,5 q_i of row o (step parity)  6 dm/al of row r
+// 7 dm/al of row o  8 xfx*fx2  9 (fx+fx2)*mfx
+constexpr int A5_XROWS = 10;
+enum : int { A5X_Q = 0, A5X_QI = 4, A5X_DR = 6, A5X_DO = 7, A5X_SF1 = 8, A5X_SFT = 9 };
+// private per-thread slots (A5_GW apart): 0..3 qy of the corner rows (step mod 4)  4..7 inner x flux of the last four rows
+// 8,9 / 10,11 tile-edge values of the inner / outer y stream  12,13 inner y flux  14,15 q of the output row (step parity)
+enum : int { A5V_QY = 0, A5V_FX2 = 4, A5V_EIN = 8, A5V_EOU = 10, A5V_FY2 = 12, A5V_QO = 14, A5V_N = 16 };
 constexpr int A5_MAXTG = 9;   // 1 + 2*9 = 19 warps -> 96 registers per thread at one CTA per SM
 
 // padded row pitch of the scratch planes: a multiple of 16 bytes in fp32 and fp64 (TMA global strides)
@@ -40,8 +46,7 @@ enum : int { A5_RX = 0, A5_MFX = 1, A5_RY = 2, A5_MFY = 3, A5_AR = 4, A5_AO = 5,
 template <class T> struct A5Stage {
   static constexpr int PAIR_BYTES = A5_NPAIR * A5_R * A5_GW * 2 * (int)sizeof(T);
   static constexpr int BYTES = PAIR_BYTES + A5_NSC * A5_R * A5_GW * (int)sizeof(T);
-  // exchange rows + per-thread private slots: 2 qy (corner rows), 4 delayed inner x fluxes, 2x2 tile-edge values of the y streams
-  static constexpr int PRIV = 10;
+  static constexpr int PRIV = A5V_N;
   static constexpr int GROUP_ELEMS = A5_XROWS * A5_XP + PRIV * A5_GW;
   static constexpr int BAR_OFF = A5_NS * BYTES;
   static constexpr int GROUP_OFF = BAR_OFF + 128;
@@ -210,12 +215,10 @@ template <class T, int OI, int OO> struct Adv5State {
   YWin<T, OI> yin;
   YWin<T, OO> you;
   T Fy_prev, fys_prev;  // yfx*fy2 / (fy+fy2)*mfy at the previous y-face
-  T fy2_c;              // inner y flux of the current row step (crosses its barriers)
   const T* qg;          // this thread's (clamped) column of q, row -2
   T* qo;
   T* smt;               // this thread's slot of exchange row 0
-  T* qys;               // this thread's private slots (A5_GW apart): 0,1 qy by row parity; 2..5 inner x flux of the last four
-                        // rows; 6,7 / 8,9 tile-edge values of the inner / outer y stream
+  T* qys;               // this thread's private slot 0 (A5V_*)
 };
 
 // per-thread view of the staged box of the current block of four row steps
@@ -255,7 +258,7 @@ template <class T, int OI, int OO>
 FV3T_HD void adv5_init(const Adv5Params<T>& p, const Adv5Cta& c, const Adv3Thr& t, T* group_smem, Adv5State<T, OI, OO>& s) {
   s.yin.init();
   s.you.init();
-  s.Fy_prev = s.fys_prev = s.fy2_c = T(0);
+  s.Fy_prev = s.fys_prev = T(0);
   s.qg = p.qin + c.qoff + t.pix;
   s.qo = p.qout + c.qoff + t.pix;
   keep_ptr(s.qg);
@@ -265,13 +268,14 @@ FV3T_HD void adv5_init(const Adv5Params<T>& p, const Adv5Cta& c, const Adv3Thr& 
   for (int k = 0; k < A5Stage<T>::PRIV; ++k) s.qys[k * A5_GW] = T(0);
 }
 
-// asynchronous copy of q(i, r) into exchange row d; CORNER: rows outside 1..n also fetch the dir = 2 view into the private slot
-// (the x sweeps see the dir = 1 corner view of q, the y sweeps the dir = 2 view: copy_corners, tp_core.F90:265-328)
-template <class T, int OI, int OO, bool CORNER>
-FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r, int d) {
+// asynchronous copy of q(i, r) into its exchange row (slot PH = row step mod 4); CORNER: rows outside 1..n also fetch the dir = 2
+// view into the private slot (the x sweeps see the dir = 1 corner view of q, the y sweeps the dir = 2 view: copy_corners,
+// tp_core.F90:265-328)
+template <class T, int OI, int OO, int PH, bool CORNER>
+FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd, npx = c.npx;
   if (!CORNER) {
-    async_copy<sizeof(T)>(A5XROW(s, d), s.qg + (r + 2) * nd);
+    async_copy<sizeof(T)>(A5XROW(s, A5X_Q + PH), s.qg + (r + 2) * nd);
   } else {
     r = r > n + 3 ? n + 3 : r;
     const int i = t.i;
@@ -290,36 +294,41 @@ FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3T
       ox = (s1j + 2) * nd + (s1i - i);
       oy = (s2j + 2) * nd + (s2i - i);
     }
-    async_copy<sizeof(T)>(A5XROW(s, d), s.qg + ox);
-    if (r < 1 || r > n) async_copy<sizeof(T)>(s.qys + d * A5_GW, s.qg + oy);
+    async_copy<sizeof(T)>(A5XROW(s, A5X_Q + PH), s.qg + ox);
+    if (r < 1 || r > n) async_copy<sizeof(T)>(s.qys + (A5V_QY + PH) * A5_GW, s.qg + oy);
   }
   async_commit();
 }
 
-// phase 1: inner y sweep (flux at y-face c = r-2), q_i of row o = r-3 to shared memory
+// The four phases of row step r (PH = step mod 4 selects the staged box row, the exchange-row slots and the window rotation):
+//   phase 1  inner y sweep (flux at y-face c = r-2), q_i of row o = r-3                          reads q row PH (own slot)
+//   phase 2  dm (ORD >= 7) / al (ORD < 7) of row r (inner x sweep) and of row o (outer x sweep on q_i)
+//   phase 3  x-face fluxes: inner sweep of row r (-> xfx*fx2), outer sweep of row o (-> (fx+fx2)*mfx)
+//   phase 4  q_j of row r, outer y sweep (flux at y-face c), flux-form update of row o
+// Dependencies inside a step: 1 -> 2 -> 3 -> 4 through the exchange rows.  Phases 1 and 4 (y direction, register-resident
+// windows) never touch what phases 2 and 3 (x direction, shared-memory rows) write in the same interval, which is what the
+// software-pipelined schedule of adv5_block uses.
 template <class T, int OI, int OO, int PH, bool YE>
 FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
-  constexpr int d = PH & 1;
   const int nd = c.nd;
   const int cc = r - 2;
   const Pair<T> y2 = A5P(v, A5_Y2, PH);  // zero outside the faces 1..n+1 (k_prep5, TMA zero fill)
   const T* dya = p.dya + c.tileoff + t.pix;
   auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
-  T qy = A5XROW(s, d)[0];
-  if (YE && (r < 1 || r > c.n)) qy = s.qys[d * A5_GW];
+  T qy = A5XROW(s, A5X_Q + PH)[0];
+  if (YE && (r < 1 || r > c.n)) qy = s.qys[(A5V_QY + PH) * A5_GW];
   const T q_o = s.yin.template q_cm1<PH>();
-  const T fy2_c = s.yin.template push<PH, YE>(cc, qy, y2.a, c.npx, p.lim_fac, met_y, s.qys + 6 * A5_GW, A5_GW);
+  const T fy2_c = s.yin.template push<PH, YE>(cc, qy, y2.a, c.npx, p.lim_fac, met_y, s.qys + A5V_EIN * A5_GW, A5_GW);
   const T Fy_c = y2.b * fy2_c;
   const T qi = (q_o * A5S(v, A5_AO, PH) + s.Fy_prev - Fy_c) * A5S(v, A5_RY, PH);  // only rows o = 1..n are consumed
   s.Fy_prev = Fy_c;
-  s.fy2_c = fy2_c;
-  A5XROW(s, 3)[0] = qi;
+  s.qys[(A5V_FY2 + (PH & 1)) * A5_GW] = fy2_c;  // phase 4 of this step runs after phase 1 of the next one
+  s.qys[(A5V_QO + (PH & 1)) * A5_GW] = q_o;
+  A5XROW(s, A5X_QI + (PH & 1))[0] = qi;
 }
 
-// phase 2: dm (ORD >= 7) or al (ORD < 7) of row r (inner x sweep) and of row o (outer x sweep on q_i)
 template <class T, int OI, int OO, int PH, bool XE>
 FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
-  constexpr int d = PH & 1;
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
@@ -327,18 +336,16 @@ FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const T* dxa = p.dxa + c.tileoff + 2;
   auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
-  const T* sqa = A5XROW(s, d) - i;  // indexable by the global column
-  const T* sqb = A5XROW(s, 3) - i;
+  const T* sqa = A5XROW(s, A5X_Q + PH) - i;  // indexable by the global column
+  const T* sqb = A5XROW(s, A5X_QI + (PH & 1)) - i;
   auto qa = [&](int gi) -> T { return sqa[gi]; };
   auto qb = [&](int gi) -> T { return sqb[gi]; };
-  A5XROW(s, 2)[0] = ppm_pre<T, OI, XE>(i, c.npx, qa, dxa_r);
-  A5XROW(s, 4)[0] = ppm_pre<T, OO, XE>(i, c.npx, qb, dxa_o);
+  A5XROW(s, A5X_DR)[0] = ppm_pre<T, OI, XE>(i, c.npx, qa, dxa_r);
+  A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, c.npx, qb, dxa_o);
 }
 
-// phase 3: x-face fluxes: inner sweep of row r (-> xfx*fx2), outer sweep of row o (-> (fx+fx2)*mfx)
 template <class T, int OI, int OO, int PH, bool XE>
 FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
-  constexpr int d = PH & 1;
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
@@ -346,40 +353,44 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const T* dxa = p.dxa + c.tileoff + 2;
   auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
-  const T *sqa = A5XROW(s, d) - i, *sda = A5XROW(s, 2) - i, *sqb = A5XROW(s, 3) - i, *sdb = A5XROW(s, 4) - i;
+  const T *sqa = A5XROW(s, A5X_Q + PH) - i, *sda = A5XROW(s, A5X_DR) - i, *sqb = A5XROW(s, A5X_QI + (PH & 1)) - i, *sdb = A5XROW(s, A5X_DO) - i;
   auto qa = [&](int gi) -> T { return sqa[gi]; };
   auto aa = [&](int gi) -> T { return sda[gi]; };
   auto qb = [&](int gi) -> T { return sqb[gi]; };
   auto ab = [&](int gi) -> T { return sdb[gi]; };
   const Pair<T> x2r = A5P(v, A5_XR, PH);
   const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, c.npx, p.lim_fac, qa, aa, dxa_r);
-  A5XROW(s, 5)[0] = x2r.b * fx2;
+  A5XROW(s, A5X_SF1)[0] = x2r.b * fx2;
   const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, c.npx, p.lim_fac, qb, ab, dxa_o);
-  A5XROW(s, 6)[0] = (fxo + s.qys[(2 + ((PH + 1) & 3)) * A5_GW]) * A5S(v, A5_MFX, PH);  // fx2 of row r-3, stored three row steps ago
-  s.qys[(2 + (PH & 3)) * A5_GW] = fx2;
+  A5XROW(s, A5X_SFT)[0] = (fxo + s.qys[(A5V_FX2 + ((PH + 1) & 3)) * A5_GW]) * A5S(v, A5_MFX, PH);  // fx2 of row r-3, stored three row steps ago
+  s.qys[(A5V_FX2 + PH) * A5_GW] = fx2;
 }
 
-// phase 4: q_j of row r, outer y sweep (flux at y-face c), flux-form update of row o
 template <class T, int OI, int OO, int PH, bool YE>
 FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
-  constexpr int d = PH & 1;
   const int n = c.n, nd = c.nd;
   const int cc = r - 2, o = r - 3;
   const T* dya = p.dya + c.tileoff + t.pix;
   auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
-  const T* sf1 = A5XROW(s, 5);
-  const T* sft = A5XROW(s, 6);
-  const T qx = A5XROW(s, d)[0];
-  const T q_o = s.yin.template q_cm1<PH>();  // the inner stream keeps q(c-1) = q(o) in slot PH+1 until the next push
+  const T* sf1 = A5XROW(s, A5X_SF1);
+  const T* sft = A5XROW(s, A5X_SFT);
+  const T qx = A5XROW(s, A5X_Q + PH)[0];
+  const T q_o = s.qys[(A5V_QO + (PH & 1)) * A5_GW];
   const T qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) * A5S(v, A5_RX, PH);
-  const T fyo_c = s.you.template push<PH, YE>(cc, qj, A5P(v, A5_Y2, PH).a, c.npx, p.lim_fac, met_y, s.qys + 8 * A5_GW, A5_GW);
-  const T fys_c = (fyo_c + s.fy2_c) * A5S(v, A5_MFY, PH);  // mfy is zero outside the faces 1..n+1
+  const T fyo_c = s.you.template push<PH, YE>(cc, qj, A5P(v, A5_Y2, PH).a, c.npx, p.lim_fac, met_y, s.qys + A5V_EOU * A5_GW, A5_GW);
+  const T fys_c = (fyo_c + s.qys[(A5V_FY2 + (PH & 1)) * A5_GW]) * A5S(v, A5_MFY, PH);  // mfy is zero outside the faces 1..n+1
   const Pair<T> ab = A5P(v, A5_CAB, PH);
   const T qnew = q_o * ab.a + (sft[0] - sft[1] + s.fys_prev - fys_c) * ab.b;
   const bool o_ok = !YE || (o >= 1 && o <= n);
   if (o_ok && t.cell) s.qo[(o + 2) * nd] = qnew;
   s.fys_prev = fys_c;
 }
+
+// number of four-row blocks: rows -2 .. n+3 plus at least one padding step (the schedule runs phase 4 one step late)
+FV3T_HD int a5_nblocks(int n) { return (n + 6) / A5_R + 1; }
+// a block whose phases all see interior cells c = r-2 (3 <= c <= npx-3) and corner-free q rows: phase 4 runs for rows r0-1 ..
+// r0+2, phases 2 and 3 for r0 .. r0+3, phase 1 for r0+1 .. r0+4, q is requested for r0+2 .. r0+5
+FV3T_HD bool a5_block_interior(int r0, int n) { return r0 >= 6 && r0 + 5 <= n; }
 
 // host restatement of what the producer warp's TMA boxes deliver for block b of (strip, level): test infrastructure
 // (tests/hostsim) and documentation of the box coordinates in one place
@@ -428,31 +439,70 @@ __device__ __forceinline__ void a5_tma_3d(void* dst, const CUtensorMap* m, int x
                "l"(m), "r"(a5_smem_u32(bar)), "r"(x), "r"(y), "r"(z)
                : "memory");
 }
-__device__ __forceinline__ void a5_group_sync(int g) {  // named barrier of one tracer group (ids 1..A5_MAXTG; 0 is __syncthreads)
-  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(A5_GW) : "memory");
+// named barrier of one tracer group (ids 1..A5_MAXTG; 0 is __syncthreads).  ONEG (one tracer per CTA): a constant id, so that
+// ptxas reserves two hardware barriers instead of all sixteen and several such CTAs share an SM.
+template <bool ONEG> __device__ __forceinline__ void a5_group_sync(int g) {
+  if (ONEG)
+    asm volatile("bar.sync 1, %0;" ::"n"(A5_GW) : "memory");
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(A5_GW) : "memory");
 }
 
-// four row steps of one block
-template <class T, int OI, int OO, int PH, bool YE, bool XE>
-__device__ __forceinline__ void adv5_step(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
-                                          const A5View<T>& v, int r, int g) {
-  async_wait_all();                                              // q of row r (requested one row step ago) has landed
-  adv5_issue_q<T, OI, OO, YE>(c, s, t, r + 1, (PH & 1) ^ 1);     // request q of row r+1
-  adv5_phase1<T, OI, OO, PH, YE>(p, c, s, t, v, r);
-  a5_group_sync(g);
-  adv5_phase2<T, OI, OO, PH, XE>(p, c, s, t, r);
-  a5_group_sync(g);
-  adv5_phase3<T, OI, OO, PH, XE>(p, c, s, t, v, r);
-  a5_group_sync(g);
-  adv5_phase4<T, OI, OO, PH, YE>(p, c, s, t, v, r);
-}
-template <class T, int OI, int OO, bool YE, bool XE>
+// One block = four row steps, software-pipelined over two barrier intervals per step:
+//     interval 1:  phase 2 of step s   |  phase 4 of step s-1        (x direction | y direction: independent instruction streams)
+//     interval 2:  phase 3 of step s   |  phase 1 of step s+1
+// Two barriers per row step instead of three and two independent dependency chains between them: k_advect5's first version
+// (phases 1-2-3-4 in sequence, three barriers) spent 2.6 of 9.4 stall cycles per issued instruction waiting on fixed-latency
+// FP64 dependencies and 0.8 at barriers (profiles/r02_advect5_v1_ncu.txt).  vp / v / vn: staged boxes of the previous, this and
+// the next block (phase 4 of step r0-1 reads the previous box, phase 1 of step r0+4 the next one).
+template <class T, int OI, int OO, bool YE, bool XE, bool ONEG>
 __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
-                                           const A5View<T>& v, int r0, int g) {
-  adv5_step<T, OI, OO, 0, YE, XE>(p, c, s, t, v, r0, g);
-  adv5_step<T, OI, OO, 1, YE, XE>(p, c, s, t, v, r0 + 1, g);
-  adv5_step<T, OI, OO, 2, YE, XE>(p, c, s, t, v, r0 + 2, g);
-  adv5_step<T, OI, OO, 3, YE, XE>(p, c, s, t, v, r0 + 3, g);
+                                           const A5View<T>& vp, const A5View<T>& v, const unsigned char* next_stage, uint64_t* full_next,
+                                           unsigned par_next, uint64_t* empty_prev, int r0, int g, int gtid) {
+  // ---- step r0 (PH 0)
+  adv5_issue_q<T, OI, OO, 2, YE>(c, s, t, r0 + 2);
+  async_wait_pending<1>();  // q of row r0+1 has landed (r0 landed one step ago)
+  adv5_phase2<T, OI, OO, 0, XE>(p, c, s, t, r0);
+  if (!YE || r0 > -2) adv5_phase4<T, OI, OO, 3, YE>(p, c, s, t, vp, r0 - 1);
+  if (empty_prev) {  // the previous box is free for the producer
+    __syncwarp();
+    if ((gtid & 31) == 0) a5_mbar_arrive(empty_prev);
+  }
+  a5_group_sync<ONEG>(g);
+  adv5_phase3<T, OI, OO, 0, XE>(p, c, s, t, v, r0);
+  adv5_phase1<T, OI, OO, 1, YE>(p, c, s, t, v, r0 + 1);
+  a5_group_sync<ONEG>(g);
+  // ---- step r0+1 (PH 1)
+  adv5_issue_q<T, OI, OO, 3, YE>(c, s, t, r0 + 3);
+  async_wait_pending<1>();
+  adv5_phase2<T, OI, OO, 1, XE>(p, c, s, t, r0 + 1);
+  adv5_phase4<T, OI, OO, 0, YE>(p, c, s, t, v, r0);
+  a5_group_sync<ONEG>(g);
+  adv5_phase3<T, OI, OO, 1, XE>(p, c, s, t, v, r0 + 1);
+  adv5_phase1<T, OI, OO, 2, YE>(p, c, s, t, v, r0 + 2);
+  a5_group_sync<ONEG>(g);
+  // ---- step r0+2 (PH 2)
+  adv5_issue_q<T, OI, OO, 0, YE>(c, s, t, r0 + 4);
+  async_wait_pending<1>();
+  adv5_phase2<T, OI, OO, 2, XE>(p, c, s, t, r0 + 2);
+  adv5_phase4<T, OI, OO, 1, YE>(p, c, s, t, v, r0 + 1);
+  a5_group_sync<ONEG>(g);
+  adv5_phase3<T, OI, OO, 2, XE>(p, c, s, t, v, r0 + 2);
+  adv5_phase1<T, OI, OO, 3, YE>(p, c, s, t, v, r0 + 3);
+  a5_group_sync<ONEG>(g);
+  // ---- step r0+3 (PH 3)
+  adv5_issue_q<T, OI, OO, 1, YE>(c, s, t, r0 + 5);
+  async_wait_pending<1>();
+  adv5_phase2<T, OI, OO, 3, XE>(p, c, s, t, r0 + 3);
+  adv5_phase4<T, OI, OO, 2, YE>(p, c, s, t, v, r0 + 2);
+  a5_group_sync<ONEG>(g);
+  adv5_phase3<T, OI, OO, 3, XE>(p, c, s, t, v, r0 + 3);
+  if (full_next) {
+    a5_mbar_wait(full_next, par_next);
+    const A5View<T> vn = a5_view<T>(next_stage, gtid);
+    adv5_phase1<T, OI, OO, 0, YE>(p, c, s, t, vn, r0 + 4);
+  }
+  a5_group_sync<ONEG>(g);
 }
 
 template <class T, int OI, int OO, int NTHR, int MINB>
@@ -476,7 +526,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const int nblocks = (n + 6 + A5_R - 1) / A5_R;
+  const int nblocks = a5_nblocks(n);
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
     // ---- producer: one thread streams the level fields of the strip through the ring
@@ -519,27 +569,38 @@ __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ 
   Adv5State<T, OI, OO> s;
   T* gsm = reinterpret_cast<T*>(smem5 + S::GROUP_OFF) + (size_t)g * S::GROUP_ELEMS;
   adv5_init<T, OI, OO>(p, c, t, gsm, s);
-  adv5_issue_q<T, OI, OO, true>(c, s, t, -2, 0);
+  constexpr bool ONEG = NTHR == 32 + A5_GW;
+  adv5_issue_q<T, OI, OO, 0, true>(c, s, t, -2);
+  adv5_issue_q<T, OI, OO, 1, true>(c, s, t, -1);
+  async_wait_all();
+  a5_mbar_wait(&full[0], 0);
+  A5View<T> v = a5_view<T>(smem5, gtid), vp = v;
+  adv5_phase1<T, OI, OO, 0, true>(p, c, s, t, v, -2);
+  a5_group_sync<ONEG>(g);
   int st = 0, wrap = 0;
   for (int b = 0; b < nblocks; ++b) {
     const int r0 = -2 + A5_R * b;
-    a5_mbar_wait(&full[st], wrap & 1);
-    const A5View<T> v = a5_view<T>(smem5 + st * S::BYTES, gtid);
-    const bool yint = r0 >= 5 && r0 + 4 <= n;  // cells c = r-2 of the block are interior (3..npx-3) and rows r+1 <= n
-    if (yint) {
+    int sn = st + 1, wn = wrap;
+    if (sn == A5_NS) {
+      sn = 0;
+      ++wn;
+    }
+    const int sp = st == 0 ? A5_NS - 1 : st - 1;
+    const unsigned char* next_stage = smem5 + sn * S::BYTES;
+    uint64_t* full_next = b + 1 < nblocks ? &full[sn] : nullptr;
+    uint64_t* empty_prev = b > 0 ? &empty[sp] : nullptr;
+    if (a5_block_interior(r0, n)) {
       if (c.xedge)
-        adv5_block<T, OI, OO, false, true>(p, c, s, t, v, r0, g);
+        adv5_block<T, OI, OO, false, true, ONEG>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
       else
-        adv5_block<T, OI, OO, false, false>(p, c, s, t, v, r0, g);
+        adv5_block<T, OI, OO, false, false, ONEG>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
     } else {
-      adv5_block<T, OI, OO, true, true>(p, c, s, t, v, r0, g);
+      adv5_block<T, OI, OO, true, true, ONEG>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
     }
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) a5_mbar_arrive(&empty[st]);
-    if (++st == A5_NS) {
-      st = 0;
-      ++wrap;
-    }
+    vp = v;
+    v = a5_view<T>(next_stage, gtid);
+    st = sn;
+    wrap = wn;
   }
   async_wait_all();
 }

@@ -977,7 +977,7 @@ int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const
     ev_done.push_back(b);
   }
   nq_cur = nq;
-  if ((rc = prepare(hord, false))) return rc;  // k_prep3 (nsplt == 1: nothing is scaled in place); per-tracer launches: k_advect4
+  if ((rc = prepare(hord))) return rc;  // k_prep5 / k_prep3 (nsplt == 1: nothing is scaled in place)
   if ((rc = remap_alloc())) return rc;
   const int c0 = cur;                   // per tracer: advect q[c0] -> q[c0^1], remap q[c0^1] -> q[c0]
   fv3t::Remap3Params<T> rp{q[c0 ^ 1], q[c0], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, nq, nt, fill};
@@ -998,30 +998,57 @@ int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const
       fv3t::k_halo_fill<T><<<grid, 256, 0, stream>>>(q[c0], halo_dst, halo_src, halo_len, n, npz, nq, ksplt_d, 1, iq * npz);
       ++launches;
     }
-    fv3t::Adv3Params<T> p;
-    p.qin = q[c0];
-    p.qout = q[c0 ^ 1];
-    p.X2 = X2;
-    p.Y2 = Y2;
-    p.rrx = rrx;
-    p.rry = rry;
-    p.cab = cab;
-    p.mfx = mfx;
-    p.mfy = mfy;
-    p.area = area;
-    p.dxa = dxa;
-    p.dya = dya;
-    p.ksplt = ksplt_d;
-    p.n = n;
-    p.npz = npz;
-    p.nq = nq;
-    p.ntiles = nt;
-    p.it = 1;
-    p.W = 0;
-    p.lim_fac = lim_fac;
-    p.iq0 = iq;
-    p.nql = 1;
-    CK(fv3t::fast_advect3<T>(p, hord, NT, stream));
+    if (call5) {
+      fv3t::Adv5Params<T> p{};
+      p.qin = q[c0];
+      p.qout = q[c0 ^ 1];
+      p.X2 = X5;
+      p.Y2 = Y5;
+      p.CAB = C5;
+      p.RX = RX5;
+      p.RY = RY5;
+      p.MFX = MX5;
+      p.MFY = MY5;
+      p.AREA = AREA5;
+      p.dxa = dxa;
+      p.dya = dya;
+      p.ksplt = ksplt_d;
+      p.n = n;
+      p.npz = npz;
+      p.nq = nq;
+      p.ntiles = nt;
+      p.it = 1;
+      p.lev0 = 0;
+      p.iq0 = iq;
+      p.nql = 1;
+      p.lim_fac = lim_fac;
+      CK(fv3t::fast_advect5<T>(p, maps5, hord, nt * npz, stream));
+    } else {
+      fv3t::Adv3Params<T> p;
+      p.qin = q[c0];
+      p.qout = q[c0 ^ 1];
+      p.X2 = X2;
+      p.Y2 = Y2;
+      p.rrx = rrx;
+      p.rry = rry;
+      p.cab = cab;
+      p.mfx = mfx;
+      p.mfy = mfy;
+      p.area = area;
+      p.dxa = dxa;
+      p.dya = dya;
+      p.ksplt = ksplt_d;
+      p.n = n;
+      p.npz = npz;
+      p.nq = nq;
+      p.ntiles = nt;
+      p.it = 1;
+      p.W = 0;
+      p.lim_fac = lim_fac;
+      p.iq0 = iq;
+      p.nql = 1;
+      CK(fv3t::fast_advect3<T>(p, hord, NT, stream));
+    }
     rp.iq0 = iq;
     rp.nql = 1;
     CK(fv3t::fast_remap3<T>(rp, ak0, stream));

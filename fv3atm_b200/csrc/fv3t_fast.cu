@@ -123,7 +123,8 @@ template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T
 
 template <class T, int OI, int OO, int TGC> static cudaError_t launch5(const Adv5Params<T>& p, const Adv5Maps& m, dim3 grid, cudaStream_t stream) {
   constexpr int NTHR = 32 + A5_GW * TGC;
-  constexpr int MINB = 1;  // the named barriers of the tracer groups take all 16 hardware barriers: one CTA per SM
+  // the named barriers of the tracer groups take all 16 hardware barriers: one CTA per SM; a one-tracer CTA uses one (two CTAs per SM)
+  constexpr int MINB = TGC == 1 ? 2 : 1;
   const size_t smem = A5Stage<T>::smem_bytes(p.tg);
   cudaError_t e = cudaFuncSetAttribute(k_advect5<T, OI, OO, NTHR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -138,6 +139,7 @@ template <class T, int OI, int OO> static cudaError_t launch5_ord(Adv5Params<T>&
   p.tg = (p.nql + chunks - 1) / chunks;
   const int strips = (p.n + A5_W - 1) / A5_W;
   dim3 grid(strips, nlev, chunks);
+  if (p.tg == 1) return launch5<T, OI, OO, 1>(p, m, grid, stream);
   if (p.tg > 5) return launch5<T, OI, OO, 9>(p, m, grid, stream);
   return launch5<T, OI, OO, 5>(p, m, grid, stream);
 }

@@ -41,32 +41,39 @@ template <class T> static void fill_stage(const Adv5Params<T>& p, int strip, int
       }
 }
 
-template <class T, int OI, int OO, int PH, bool YE, bool XE>
-static void sim_step(const Adv5Params<T>& p, const Adv5Cta& c, std::vector<Adv5State<T, OI, OO>>& st, const std::vector<Adv3Thr>& th,
-                     const unsigned char* stage, int r) {
-  const int NT = A5_GW;
-  for (int tid = 0; tid < NT; ++tid) {
-    adv5_issue_q<T, OI, OO, YE>(c, st[tid], th[tid], r + 1, (PH & 1) ^ 1);
-    adv5_phase1<T, OI, OO, PH, YE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
+// one block of four row steps in the product's two-interval schedule (adv5_block): interval 1 = phase 2 of step s + phase 4 of
+// step s-1, interval 2 = phase 3 of step s + phase 1 of step s+1; a barrier (= end of a loop over the threads) after each
+template <class T, int OI, int OO> struct Sim {
+  const Adv5Params<T>& p;
+  const Adv5Cta& c;
+  std::vector<Adv5State<T, OI, OO>>& st;
+  const std::vector<Adv3Thr>& th;
+
+  template <int PH, int PHQ, bool YE, bool XE, int PH4, int PH1>
+  void step(const unsigned char* stage4, const unsigned char* stage, const unsigned char* stage1, int r, bool do4, bool do1) {
+    for (int tid = 0; tid < A5_GW; ++tid) {
+      adv5_issue_q<T, OI, OO, PHQ, YE>(c, st[tid], th[tid], r + 2);
+      adv5_phase2<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], r);
+      if (do4) adv5_phase4<T, OI, OO, PH4, YE>(p, c, st[tid], th[tid], a5_view<T>(stage4, tid), r - 1);
+    }
+    for (int tid = 0; tid < A5_GW; ++tid) {
+      adv5_phase3<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
+      if (do1) adv5_phase1<T, OI, OO, PH1, YE>(p, c, st[tid], th[tid], a5_view<T>(stage1, tid), r + 1);
+    }
   }
-  for (int tid = 0; tid < NT; ++tid) adv5_phase2<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], r);
-  for (int tid = 0; tid < NT; ++tid) adv5_phase3<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
-  for (int tid = 0; tid < NT; ++tid) adv5_phase4<T, OI, OO, PH, YE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
-}
-template <class T, int OI, int OO, bool YE, bool XE>
-static void sim_block(const Adv5Params<T>& p, const Adv5Cta& c, std::vector<Adv5State<T, OI, OO>>& st, const std::vector<Adv3Thr>& th,
-                      const unsigned char* stage, int r0) {
-  sim_step<T, OI, OO, 0, YE, XE>(p, c, st, th, stage, r0);
-  sim_step<T, OI, OO, 1, YE, XE>(p, c, st, th, stage, r0 + 1);
-  sim_step<T, OI, OO, 2, YE, XE>(p, c, st, th, stage, r0 + 2);
-  sim_step<T, OI, OO, 3, YE, XE>(p, c, st, th, stage, r0 + 3);
-}
+  template <bool YE, bool XE> void block(const unsigned char* sp, const unsigned char* sc, const unsigned char* sn, int r0) {
+    step<0, 2, YE, XE, 3, 1>(sp, sc, sc, r0, !YE || r0 > -2, true);
+    step<1, 3, YE, XE, 0, 2>(sc, sc, sc, r0 + 1, true, true);
+    step<2, 0, YE, XE, 1, 3>(sc, sc, sc, r0 + 2, true, true);
+    step<3, 1, YE, XE, 2, 0>(sc, sc, sn, r0 + 3, true, sn != nullptr);
+  }
+};
 
 template <class T, int OI, int OO> static void run_substep(const Adv5Params<T>& p) {
   const int n = p.n;
   const int strips = (n + A5_W - 1) / A5_W;
-  const int nblocks = (n + 6 + A5_R - 1) / A5_R;
-  std::vector<unsigned char> stage(A5Stage<T>::BYTES + 16);
+  const int nblocks = a5_nblocks(n);
+  std::vector<unsigned char> stage(A5_NS * A5Stage<T>::BYTES + 16);
   unsigned char* sg = stage.data() + ((16 - ((uintptr_t)stage.data() & 15)) & 15);
   std::vector<T> gsm(A5Stage<T>::GROUP_ELEMS + 2);
   T* gs = gsm.data() + (((uintptr_t)gsm.data() & 15) ? 1 : 0);
@@ -77,22 +84,31 @@ template <class T, int OI, int OO> static void run_substep(const Adv5Params<T>& 
       for (int iq = p.iq0; iq < p.iq0 + p.nql; ++iq) {
         Adv5Cta c;
         if (!adv5_make_cta<T>(p, strip, levc, iq, c)) continue;
+        Sim<T, OI, OO> sim{p, c, st, th};
+        fill_stage<T>(p, strip, levc, 0, sg);
         for (int tid = 0; tid < A5_GW; ++tid) {
           th[tid] = adv5_thread(c, tid);
           adv5_init<T, OI, OO>(p, c, th[tid], gs, st[tid]);
-          adv5_issue_q<T, OI, OO, true>(c, st[tid], th[tid], -2, 0);
+          adv5_issue_q<T, OI, OO, 0, true>(c, st[tid], th[tid], -2);
+          adv5_issue_q<T, OI, OO, 1, true>(c, st[tid], th[tid], -1);
+          adv5_phase1<T, OI, OO, 0, true>(p, c, st[tid], th[tid], a5_view<T>(sg, tid), -2);
         }
         for (int b = 0; b < nblocks; ++b) {
           const int r0 = -2 + A5_R * b;
-          fill_stage<T>(p, strip, levc, b, sg);
-          const bool yint = r0 >= 5 && r0 + 4 <= n;
-          if (yint) {
+          unsigned char* sc = sg + (b % A5_NS) * A5Stage<T>::BYTES;
+          unsigned char* sp = sg + ((b + A5_NS - 1) % A5_NS) * A5Stage<T>::BYTES;
+          unsigned char* sn = nullptr;
+          if (b + 1 < nblocks) {  // the producer is (at least) one box ahead
+            sn = sg + ((b + 1) % A5_NS) * A5Stage<T>::BYTES;
+            fill_stage<T>(p, strip, levc, b + 1, sn);
+          }
+          if (a5_block_interior(r0, n)) {
             if (c.xedge)
-              sim_block<T, OI, OO, false, true>(p, c, st, th, sg, r0);
+              sim.template block<false, true>(sp, sc, sn, r0);
             else
-              sim_block<T, OI, OO, false, false>(p, c, st, th, sg, r0);
+              sim.template block<false, false>(sp, sc, sn, r0);
           } else {
-            sim_block<T, OI, OO, true, true>(p, c, st, th, sg, r0);
+            sim.template block<true, true>(sp, sc, sn, r0);
           }
         }
       }
