@@ -425,12 +425,12 @@ __device__ __forceinline__ void a5_mbar_wait(uint64_t* b, unsigned parity) {
       "{\n"
       ".reg .pred p;\n"
       "A5_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra A5_DONE_%=;\n"
       "bra A5_WAIT_%=;\n"
       "A5_DONE_%=:\n"
       "}\n" ::"r"(a5_smem_u32(b)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint: let the hardware park the warp instead of spinning through try_wait
       : "memory");
 }
 __device__ __forceinline__ void a5_tma_3d(void* dst, const CUtensorMap* m, int x, int y, int z, uint64_t* bar) {

@@ -141,6 +141,9 @@ template <class T> struct Impl {
   bool scale_pending = false;  // k_advect5 path: the in-place 1/ksplt scaling of cx, cy, mfx, mfy is applied by finish()
   fv3t::Pair<T>* P1 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
   T *GAM = nullptr, *RD1 = nullptr, *R2 = nullptr;
+  unsigned char* coef4 = nullptr;  // lanes-over-levels remap (fv3t_remap4.cuh): per-column-group coefficient blocks
+  unsigned char* neg4 = nullptr;   // per column and tracer: the remapped column holds a negative value (k_fillz4)
+  bool use4 = false;               // FV3T_REMAP4=1 selects the experimental lanes-over-levels kernel (kord 9; slower on B200)
   cudaStream_t side = nullptr;            // remap_prepare: the coefficient kernel runs here, concurrently with tracer_2d
   cudaEvent_t ev_fork = nullptr, ev_coef = nullptr;
   bool coef_ready = false, coef_wanted = false;
@@ -239,6 +242,7 @@ template <class T> struct Impl {
   int tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const T* hpe, const T* hak, const T* hbk, T hptop, T* hdelp, int nq,
                   int hord, int q_split, T lim_fac, const int* kord, int fill, int* nsplt_out);
   int remap_alloc();
+  bool remap4_ok() const { return fast && use4 && npz <= 127; }  // (and abs(kord) == 9, checked by the caller)
 };
 
 template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g, int dev, void* strm) {
@@ -282,6 +286,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   CK(dalloc(&pe, sz_pe() * nt));
   fast = !(getenv("FV3T_STRICT") && atoi(getenv("FV3T_STRICT")) != 0);
   use5 = !(getenv("FV3T_ADV5") && atoi(getenv("FV3T_ADV5")) == 0);
+  use4 = getenv("FV3T_REMAP4") && atoi(getenv("FV3T_REMAP4")) != 0;
   CK(cudaMemsetAsync(q[0], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(q[1], 0, sz_q(nqmax) * nt * sizeof(T), stream));
   CK(cudaMemsetAsync(delp, 0, sz_c() * nt * sizeof(T), stream));
@@ -356,7 +361,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, coef4, neg4, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -829,7 +834,19 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
     const int a = kord[iq] < 0 ? -kord[iq] : kord[iq];
     fast_ok = fast_ok && fv3t::fast_kord_ok(a) && (a == ak0 || (a <= 8 && ak0 <= 8) || (a >= 17 && ak0 >= 17));
   }
-  if (fast_ok) {
+  if (fast_ok && remap4_ok() && ak0 == 9) {
+    if (!coef4) CK(cudaMalloc((void**)&coef4, fv3t::remap4_coef_bytes<T>(n, nt)));
+    if (!neg4) CK(cudaMalloc((void**)&neg4, (size_t)nt * nqmax * n * n));
+    fv3t::Remap4Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, coef4, neg4, ptop, n, npz, nq, nt, fill, 0, nq, 0, 0};
+    if (!coef_ready) {  // otherwise computed ahead by remap_prepare on the side stream (waited for above)
+      kbegin();
+      CK(fv3t::fast_remap_coef4<T>(p, stream));
+      kend(KC_SCALE);
+    }
+    kbegin();
+    CK(fv3t::fast_remap4<T>(p, ak0, stream));
+    kend(KC_REMAP);
+  } else if (fast_ok) {
     int rca = remap_alloc();
     if (rca) return rca;
     fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, nq, nt, fill};
@@ -1072,7 +1089,7 @@ int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const
 // runs.  Valid until pe, ak, bk or ptop change; the next remap_tracers_resident consumes the result.
 template <class T> int Impl<T>::remap_prepare() {
   if (!have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
-  if (!fast || npz > 128) return 0;  // strict kernels compute everything themselves
+  if (!fast || npz > 128 || use4) return 0;  // strict kernels compute everything themselves; the experimental k_remap4 has its own coefficients
   coef_wanted = true;                // launched by the next tracer_2d sub-step, right behind its bandwidth-bound preparation
   return 0;
 }
@@ -1087,12 +1104,14 @@ template <class T> int Impl<T>::launch_coef_side() {
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_coef, cudaEventDisableTiming));
   }
-  int rc = remap_alloc();
-  if (rc) return rc;
-  fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, 0, nt, 1};
   CK(cudaEventRecord(ev_fork, stream));
   CK(cudaStreamWaitEvent(side, ev_fork, 0));
-  CK(fv3t::fast_remap_coef3<T>(p, side));
+  {
+    int rc = remap_alloc();
+    if (rc) return rc;
+    fv3t::Remap3Params<T> p{q[cur], q[cur ^ 1], pe, ak, bk, delp, P1, GAM, RD1, R2, ptop, n, npz, 0, nt, 1};
+    CK(fv3t::fast_remap_coef3<T>(p, side));
+  }
   ++launches;
   CK(cudaEventRecord(ev_coef, side));
   coef_ready = true;

@@ -158,6 +158,50 @@ template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, 
   }
 }
 
+
+// ---- k_remap4 ---------------------------------------------------------------------------------------------------------------
+template <class T> size_t remap4_coef_bytes(int n, int ntiles) { return (size_t)ntiles * n * r4_groups_per_row(n) * R4Block<T>::BYTES; }
+template <class T> cudaError_t fast_remap_coef4(const Remap4Params<T>& p, cudaStream_t stream) {
+  dim3 grid((p.n * p.n + 127) / 128, p.ntiles);
+  k_remap_coef4<T><<<grid, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+template <class T, int AK, int LPL> static cudaError_t launch_remap4(Remap4Params<T>& p, cudaStream_t stream) {
+  static const int cap_env = getenv("FV3T_REMAP_TW") ? atoi(getenv("FV3T_REMAP_TW")) : R4_MAXW;  // tracer warps per CTA (tuning knob)
+  const int cap = cap_env < 1 ? 1 : (cap_env > R4_MAXW ? R4_MAXW : cap_env);
+  const int chunks = (p.nql + cap - 1) / cap;
+  p.ntw = (p.nql + chunks - 1) / chunks;
+  const long total = (long)p.ntiles * p.n * r4_groups_per_row(p.n);
+  static const int waves = getenv("FV3T_REMAP_WAVES") ? atoi(getenv("FV3T_REMAP_WAVES")) : 8;
+  long ctas = 148L * (waves < 1 ? 1 : waves);
+  if (ctas > total) ctas = total;
+  p.groups_per_cta = (int)((total + ctas - 1) / ctas);
+  ctas = (total + p.groups_per_cta - 1) / p.groups_per_cta;
+  constexpr int CB = (R4Block<T>::BYTES + 127) & ~127;
+  constexpr int WB = (R4Warp<T, LPL>::BYTES + 127) & ~127;
+  const size_t smem = (((size_t)2 * CB + 128 + 2 * 132 * sizeof(T) + 127) & ~(size_t)127) + (size_t)p.ntw * WB;
+  cudaError_t e = cudaFuncSetAttribute(k_remap4<T, AK, LPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)ctas, chunks);
+  k_remap4<T, AK, LPL><<<grid, 32 * (p.ntw + 1), smem, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || !p.fill) return e;
+  dim3 gf((p.n * p.n + 127) / 128, p.ntiles, p.nql);
+  k_fillz4<T><<<gf, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+template <class T, int AK> static cudaError_t launch_remap4_lpl(Remap4Params<T>& p, cudaStream_t stream) {
+  if (p.km <= 63) return launch_remap4<T, AK, 8>(p, stream);
+  return launch_remap4<T, AK, 16>(p, stream);
+}
+// Experimental (FV3T_REMAP4=1): instantiated for abs(kord) = 9 only -- on B200 the lanes-over-levels kernel is SLOWER than k_remap3
+// (160 ms vs 89 ms at C768 L127 x9 fp64, profiles/r02_remap4_v2_ncu.txt): its 4.4 KB of shared memory per column-tracer in
+// flight leaves ten warps per SM, too few for its dependent shuffle / shared-memory chains.
+template <class T> cudaError_t fast_remap4(Remap4Params<T> p, int akord, cudaStream_t stream) {
+  if (p.km > 127 || akord != 9) return cudaErrorInvalidValue;
+  return launch_remap4_lpl<T, 9>(p, stream);
+}
+
 template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaStream_t stream) {
   dim3 grid((p.n * p.n + 127) / 128, p.ntiles);
   k_remap_coef3<T><<<grid, 128, 0, stream>>>(p);
@@ -197,6 +241,9 @@ template <class T> cudaError_t fast_remap3(const Remap3Params<T>& p, int akord, 
   template cudaError_t fast_pad_plane<T>(T*, const T*, int, int, int, cudaStream_t);                                  \
   template cudaError_t fast_advect5_maps<T>(Adv5Maps*, const Adv5Params<T>&, int);                                    \
   template cudaError_t fast_advect5<T>(Adv5Params<T>, const Adv5Maps&, int, int, cudaStream_t);                       \
+  template size_t remap4_coef_bytes<T>(int, int);                                                                     \
+  template cudaError_t fast_remap_coef4<T>(const Remap4Params<T>&, cudaStream_t);                                     \
+  template cudaError_t fast_remap4<T>(Remap4Params<T>, int, cudaStream_t);                                            \
   template cudaError_t fast_remap_coef3<T>(const Remap3Params<T>&, cudaStream_t);                                     \
   template cudaError_t fast_remap3<T>(const Remap3Params<T>&, int, cudaStream_t);
 #if defined(FV3T_INST_F64) || !defined(FV3T_INST_F32)

@@ -8,6 +8,7 @@
 #include "fv3t_advect4.cuh"
 #include "fv3t_advect5.cuh"
 #include "fv3t_remap3.cuh"
+#include "fv3t_remap4.cuh"
 
 namespace fv3t {
 
@@ -37,5 +38,10 @@ template <class T> cudaError_t fast_pad_plane(T* dst, const T* src, int nd, int 
 template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T>& p, int nlev);
 // p.tg is chosen by the launcher; nlev = levels of the resident chunk (grid.y)
 template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
+
+// ---- lanes-over-levels remap (fv3t_remap4.cuh): km <= 127, mapn_tracer form, uniform abs(kord) in fast_kord_ok ----
+template <class T> size_t remap4_coef_bytes(int n, int ntiles);
+template <class T> cudaError_t fast_remap_coef4(const Remap4Params<T>& p, cudaStream_t stream);
+template <class T> cudaError_t fast_remap4(Remap4Params<T> p, int akord, cudaStream_t stream);
 
 }  // namespace fv3t
