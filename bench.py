@@ -51,12 +51,14 @@ def parse():
     ap.add_argument("--hord", type=int, default=8)
     ap.add_argument("--kord", type=int, default=9)
     ap.add_argument("--courant", type=float, default=0.7)
-    ap.add_argument("--shard", default="tracer", choices=["tracer", "face", "group"],
-                    help="tracer: every rank its own nq tracers (weak); face / group: ONE nq-tracer problem split by faces x tracer groups / by tracer groups only (strong)")
+    ap.add_argument("--shard", default="face", choices=["tracer", "face", "group"],
+                    help="N > 1 ranks.  face (default) / group: ONE nq-tracer problem split by faces x tracer groups / by tracer groups only "
+                         "(strong scaling, BASELINE config 4 / 5); tracer: every rank its own nq tracers (replicas, weak)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of a level subset of the workload")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-levels", type=int, default=8, help="levels of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-levels", type=int, default=0, help="levels of the bounded CPU-baseline sample (0: 2 x host threads, 8..64)")
     ap.add_argument("--cpu-n", type=int, default=0, help="tile size of the CPU sample (0: same as --n)")
     return ap.parse_args()
 
@@ -127,34 +129,124 @@ def alg_bytes(w, nq, S=1.0):
 
 # ----------------------------------------------------------------------------------------------------
 def cpu_reference_run(args, steps, warmup, quiet=False):
-    """Times the CPU oracle (all host threads) on a bounded sample: same horizontal grid / tracer count / schemes,
-    `cpu_levels` of the npz levels, one tracer_2d + one tracer remap per step."""
+    """Times the CPU oracle with ALL host threads on a bounded sample of the workload: same horizontal grid, tracer count and
+    schemes; `levels` of the npz levels with levels >= 2 x the host threads, because the oracle keeps the reference's
+    threading structure (OpenMP over k in tracer_2d, over j in the remap: fv_tracer2d.F90:503, fv_mapz.F90:250) and would
+    otherwise leave threads idle.  The sample's inputs are 8 generated levels repeated along k (levels are independent in
+    tracer_2d; the remap sees shorter columns).  Only the two oracle calls are inside the timer: inputs are restored, and the
+    halo index table is built, outside it."""
     import oracle_binding as ob
     from fv3atm_b200 import synthetic as sy, cubed_sphere as cs
     ob.build()
     n = args.cpu_n or args.n
-    npz = max(6, args.cpu_levels)
     cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
     ob.set_num_threads(cores)
+    threads = ob.max_threads()
+    levels = args.cpu_levels or max(8, min(2 * threads, 64, args.npz))
+    w = 8 if args.dtype == "float64" else 4
+    try:   # keep the sample (q twice + the level fields + the oracle's own work arrays) inside the host memory
+        import psutil
+        per_level = 6 * (n + 6) ** 2 * w * (2 * args.nq + 12)
+        levels = max(8, min(levels, int(0.5 * psutil.virtual_memory().available / per_level)))
+    except Exception:
+        pass
     grid = cs.make_grid(n)
-    case = sy.make_case(n, npz, args.nq, dtype=args.dtype, courant=args.courant, grid=grid)
+    base = sy.make_case(n, 8, args.nq, dtype=args.dtype, courant=args.courant, grid=grid)
+    reps = -(-levels // 8)
+    import copy
+    case = copy.copy(base)
+    case.npz = levels
+    tile_k = lambda a, ax: np.ascontiguousarray(np.concatenate([a] * reps, axis=ax).take(range(levels), axis=ax))
+    case.q = tile_k(base.q, 2)
+    for f in ("dp1", "mfx", "mfy", "cx", "cy"):
+        setattr(case, f, tile_k(getattr(base, f), 1))
+    case.ak, case.bk, case.ptop = sy.hybrid_coordinate(levels)
+    # Lagrangian interfaces of the short column: the Eulerian ones perturbed by a fraction of a layer, ends pinned
+    pe_e = case.ak[None, None, :, None] + case.bk[None, None, :, None] * base.pe[:, :, -1:, :]
+    wob = 0.3 * np.sin(np.arange(levels + 1) * 1.7)[None, None, :, None] * np.gradient(pe_e, axis=2)
+    wob[:, :, 0], wob[:, :, -1] = 0.0, 0.0
+    case.pe = np.ascontiguousarray((pe_e + wob).astype(args.dtype))
+    del base
     kord = np.full(args.nq, args.kord, dtype=np.int32)
-    updates = 6 * n * n * npz * args.nq
+    halo = ob.halo_offsets(n)
+    pristine = {f: getattr(case, f).copy() for f in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    delp = np.zeros_like(case.dp1)
+    updates = 6 * n * n * levels * args.nq
     times = []
     for s in range(warmup + steps):
+        for f, a in pristine.items():
+            np.copyto(getattr(case, f), a)
         t0 = time.perf_counter()
-        r = ob.tracer_2d(case, hord=args.hord)
-        ob.remap_tracers(r["q"], case.pe, case.ak, case.bk, case.ptop, kord, fill=True)
+        ob.tracer_2d(case, hord=args.hord, inplace=True, halo=halo)
+        ob.remap_tracers(case.q, case.pe, case.ak, case.bk, case.ptop, kord, fill=True, inplace=True, delp=delp)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
     t = float(np.mean(times))
-    sample = f"C{n} L{npz} of L{args.npz}, {args.nq} tracers, {args.dtype}, 1 tracer_2d + 1 tracer remap per step, includes oracle-side array copies"
-    return {"value": updates / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": t * 1e3,
+    sample = (f"C{n}, {levels} of the {args.npz} levels ({threads} OpenMP threads, OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}), "
+              f"{args.nq} tracers, {args.dtype}, 1 tracer_2d + 1 tracer remap per step; only the oracle calls are timed")
+    return {"value": updates / t, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": t * 1e3,
             "updates_per_step": updates}
 
 
+def parity_check(args, grid, device):
+    """Oracle check of the benchmarked path on the bench's own inputs: the same horizontal grid, tracers, schemes and device
+    generator with 8 of the levels (levels are independent in tracer_2d, columns in the remap).  Not timed."""
+    import oracle_binding as ob
+    from fv3atm_b200.tracer import TracerContext
+    from fv3atm_b200 import synthetic_device as sd, devarray as da
+    n, nq, npz = args.n, args.nq, 8
+    ob.build()
+    ob.set_num_threads(ob.max_threads())
+    ctx = TracerContext(n + 1, npz, nq, grid.astype(args.dtype), dtype=args.dtype, device=device)
+    ak, bk, ptop = sd.fill_context(ctx, grid, nq, courant=args.courant, seed=20260101, device=device)
+    host = {f: np.empty(da.field_shape(ctx, f, nq), dtype=args.dtype) for f in ("q", "dp1", "mfx", "mfy", "cx", "cy", "pe")}
+    for f in host:
+        ctx.download(f, host[f], nq)
+    kord = np.full(nq, args.kord, dtype=np.int32)
+    nsplt = ctx.tracer_2d_resident(nq, args.hord)
+    qadv = np.empty_like(host["q"])
+    ctx.download("q", qadv, nq)
+    ctx.remap_tracers_resident(nq, kord, fill=True)
+    q1 = np.empty_like(host["q"])
+    delp = np.empty_like(host["dp1"])
+    ctx.download("q", q1, nq)
+    ctx.download("delp", delp, nq)
+    ctx.close()
+
+    class Case:
+        pass
+    case = Case()
+    case.n, case.npz, case.nq, case.dtype = n, npz, nq, np.dtype(args.dtype)
+    for f in host:
+        setattr(case, f, host[f])
+    case.metrics = lambda: grid.astype(args.dtype)
+    ref = ob.tracer_2d(case, hord=args.hord)
+    qref, dref = ob.remap_tracers(qadv, host["pe"], ak, bk, ptop, kord, fill=True)
+    sl = slice(3, -3)
+
+    def nd(a, b):
+        d = np.abs(a[..., sl, sl].astype(np.float64) - b[..., sl, sl].astype(np.float64)).max(axis=(0, 2, 3, 4))
+        return float((d / np.maximum(np.abs(b[..., sl, sl].astype(np.float64)).max(axis=(0, 2, 3, 4)), 1e-300)).max())
+
+    tol = 1e-12 if args.dtype == "float64" else 1e-5
+    out = {"sample": f"C{n}, 8 of the {args.npz} levels, {nq} tracers, {args.dtype}, the bench's device-generated inputs, vs the CPU oracle",
+           "max_norm_diff_advect": nd(qadv, ref["q"]), "max_norm_diff_remap_of_the_advected_field": nd(q1, qref),
+           "delp_bit_identical": bool(np.array_equal(delp[..., sl, sl], dref[..., sl, sl])), "nsplt_equal": bool(nsplt == ref["nsplt"]),
+           "tolerance": tol}
+    out["ok"] = bool(out["max_norm_diff_advect"] <= tol and out["max_norm_diff_remap_of_the_advected_field"] <= tol
+                     and out["delp_bit_identical"] and out["nsplt_equal"])
+    return out
+
+
 def main():
+    # the CPU arm keeps the reference's OpenMP structure: pin its threads (read by libgomp when liboracle.so is loaded)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,6 +294,7 @@ def main():
 
     if args.shard in ("face", "group") and world > 1:
         from fv3atm_b200 import partition
+        args.clock_sampler = ClockSampler
         return partition.bench_face_sharded(args, rank, world, local_rank, prefer="face" if args.shard == "face" else "tracer")
 
     n, npz, nq = args.n, args.npz, args.nq
@@ -257,27 +350,32 @@ def main():
         rm_avg = rm_ms / max(rm_n, 1)
         strict = os.environ.get("FV3T_STRICT", "0") not in ("", "0")
         ring = os.environ.get("FV3T_ADV_RING", "1") not in ("", "0")
-        names = {"advect": "k_advect2" if strict else ("k_advect4" if ring else "k_advect3"), "remap": "k_remap2" if strict else "k_remap3"}
+        adv5 = os.environ.get("FV3T_ADV5", "1") not in ("", "0") and args.hord in (8, 10, 9, 11, 12, 13, 2) and nq >= 4
+        fast_adv = not strict and args.hord in (8, 9, 11, 12, 13, 2, 10)
+        names = {"advect": "k_advect2" if not fast_adv else ("k_advect5" if adv5 else ("k_advect4" if ring else "k_advect3")),
+                 "remap": "k_remap2" if strict else ("k_remap4" if os.environ.get("FV3T_REMAP4", "0") not in ("", "0") else "k_remap3")}
         dom = "advect" if adv_ms >= rm_ms else "remap"
         kern = names[dom]
         a_bytes, a_ms = (adv_bytes, adv_avg) if dom == "advect" else (rm_bytes, rm_avg)
         ach = a_bytes / (a_ms * 1e-3) / 1e9
         # measured DRAM bytes per launch of the same kernel at the same size, from the committed ncu capture
         traffic, tsrc = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_c768.json")))
-            if tj["config"] == {"n": n, "npz": npz, "nq": nq, "dtype": args.dtype} and kern in tj["kernels"]:
-                traffic = tj["kernels"][kern]["dram_bytes_per_launch"]
-                tsrc = "profiles/r01_traffic_c768.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-        except Exception:
-            pass
+        for tf in ("r02_traffic_c768.json", "r01_traffic_c768.json"):   # newest capture that knows this kernel at this size
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+                if tj["config"] == {"n": n, "npz": npz, "nq": nq, "dtype": args.dtype} and kern in tj["kernels"]:
+                    traffic = tj["kernels"][kern]["dram_bytes_per_launch"]
+                    tsrc = f"profiles/{tf} (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the same size)"
+                    break
+            except Exception:
+                pass
         roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": tsrc, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
                 "bytes_per_launch": a_bytes, "avg_launch_ms": a_ms,
                 "note": "fp64 path is bound by instruction issue / the FP64 pipe, not by HBM (DESIGN.md section 4)",
                 "kernels": {names["advect"]: {"avg_ms": adv_avg, "launches_per_step": adv_n / 2, "alg_GBps": adv_bytes / (adv_avg * 1e-3) / 1e9 if adv_avg else None},
                             names["remap"]: {"avg_ms": rm_avg, "launches_per_step": rm_n / 2, "alg_GBps": rm_bytes / (rm_avg * 1e-3) / 1e9 if rm_avg else None},
-                            "other_ms_per_step (k_prep3, k_remap_coef3, k_cmax, k_halo_fill)": oth / 2},
+                            "other_ms_per_step (k_prep5, k_remap_coef3, k_cmax, k_halo_fill)": oth / 2},
                 "step_alg_bytes_per_update": alg_bytes(w, nq, 1.0),
                 "step_frac_of_roofline": (value / world) * alg_bytes(w, nq, 1.0) / (peak * 1e9)}
 
@@ -344,6 +442,11 @@ def main():
                "ms_per_step": float(et.item()) / args.e2e_steps}
         del host
 
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        ctx.close()
+        parity = parity_check(args, grid, local_rank)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_reference_run(args, 1, 1)
@@ -356,7 +459,7 @@ def main():
                 "config": {"workload": workload, "parallelism": f"tracer-group x{world}" if world > 1 else "single GPU, 6 faces resident",
                            "nsplt": int(nsplt), "l2": "inputs (tens of GB) far exceed the 126 MB L2; no flush needed",
                            "updates_per_step": updates_rank * world},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         if e2e_note:
             line["e2e_note"] = e2e_note
         print(json.dumps(line))

@@ -42,10 +42,18 @@ FV3T_HD int a5_pitch(int n) { return (n + 6 + 3) & ~3; }
 
 // staged arrays of one box (A5_R rows x A5_GW columns each)
 enum : int { A5_XR = 0, A5_XO = 1, A5_Y2 = 2, A5_CAB = 3, A5_NPAIR = 4 };                           // Pair<T>
-enum : int { A5_RX = 0, A5_MFX = 1, A5_RY = 2, A5_MFY = 3, A5_AR = 4, A5_AO = 5, A5_NSC = 6 };      // T
+enum : int { A5_RX = 0, A5_MFX = 1, A5_RY = 2, A5_MFY = 3, A5_AR = 4, A5_AO = 5, A5_RA = 6, A5_NSC = 7 };  // T
 template <class T> struct A5Stage {
+  // A TMA box must start on a 16-byte boundary of global memory (the hardware raises an illegal-instruction error otherwise).
+  // Strip s starts at plane column 58 s: 464 s bytes for fp64 and for the fp32 pairs, but 232 s bytes for fp32 scalars -- their
+  // boxes start at the column rounded down to a multiple of four and are four columns wider; the lanes read at that shift.
+  static constexpr int SW = sizeof(T) == 4 ? A5_GW + 4 : A5_GW;  // columns of a scalar box
+  FV3T_HD static int shift(int xs) { return sizeof(T) == 4 ? (xs & 3) : 0; }
   static constexpr int PAIR_BYTES = A5_NPAIR * A5_R * A5_GW * 2 * (int)sizeof(T);
-  static constexpr int BYTES = PAIR_BYTES + A5_NSC * A5_R * A5_GW * (int)sizeof(T);
+  static constexpr int SBYTES = (A5_R * SW * (int)sizeof(T) + 127) & ~127;  // one scalar box (TMA destinations: 128-byte aligned)
+  static constexpr int SFIELD = SBYTES / (int)sizeof(T);
+  static constexpr int TX_BYTES = PAIR_BYTES + A5_NSC * A5_R * SW * (int)sizeof(T);  // bytes the ten boxes deliver
+  static constexpr int BYTES = PAIR_BYTES + A5_NSC * SBYTES;
   static constexpr int PRIV = A5V_N;
   static constexpr int GROUP_ELEMS = A5_XROWS * A5_XP + PRIV * A5_GW;
   static constexpr int BAR_OFF = A5_NS * BYTES;
@@ -54,7 +62,7 @@ template <class T> struct A5Stage {
 };
 
 struct alignas(64) Adv5Maps {
-  CUtensorMap x2, y2, cab, rx, ry, mfx, mfy, area;
+  CUtensorMap x2, y2, cab, rx, ry, mfx, mfy, area, rarea;
 };
 
 template <class T> struct Adv5Params {
@@ -63,7 +71,7 @@ template <class T> struct Adv5Params {
   // scratch of the resident level chunk, padded plane layout [level][row 0..nd-1][PP] (row = j+2, column = i+2)
   const Pair<T>*X2, *Y2, *CAB;
   const T *RX, *RY, *MFX, *MFY;
-  const T* AREA;        // [tile][nd][PP]
+  const T *AREA, *RAREA;  // [tile][nd][PP]
   const T *dxa, *dya;   // Fortran layout (tile-edge formulas only)
   const int* ksplt;
   int n, npz, nq, ntiles, it;
@@ -86,6 +94,7 @@ template <class T> struct Prep5Params {
   T *RX, *RY, *MFX, *MFY;
   const int* ksplt;
   int n, npz, ntiles, lev0, nlev, it, mode_all;
+  int exact;  // 1: scratch for the exact-arithmetic instantiations (ra_x, ra_y, {dp1, dp2}); 0: reciprocals and {dp1/dp2, rarea/2dp2}
 };
 
 template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, int e) {
@@ -115,9 +124,14 @@ template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, in
     }
     if (p.it <= ks) {
       const T d2 = dp2_of<T>(d1, m0, m1, m2, m3, rar);
-      const T r2 = T(1) / d2;
-      ab.a = d1 * r2;
-      ab.b = T(0.5) * rar * r2;
+      if (p.exact) {
+        ab.a = d1;
+        ab.b = d2;
+      } else {
+        const T r2 = T(1) / d2;
+        ab.a = d1 * r2;
+        ab.b = T(0.5) * rar * r2;
+      }
     }
   }
   if (p.it > ks) return;
@@ -140,7 +154,8 @@ template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, in
     if (i <= n) {
       T c1;
       const T xf1 = xfx_of<T>(cxp, dxa, dyg, ssg, plane, nd, n, i + 1, j, frac, c1);
-      rx = T(1) / add_rn(add_rn(area[e], xf), -xf1);
+      rx = add_rn(add_rn(area[e], xf), -xf1);  // ra_x (fv_tracer2d.F90:522-526)
+      if (!p.exact) rx = T(1) / rx;
     }
     if (j >= 1 && j <= n) mx = mul_rn(mxp[(long)(j - 1) * (n + 1) + (i - 1)], frac);
   }
@@ -152,7 +167,8 @@ template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, in
     if (j <= n) {
       T c1;
       const T yf1 = yfx_of<T>(cyp, dya, dxg, ssg, plane, nd, n, i, j + 1, frac, c1);
-      ry = T(1) / add_rn(add_rn(area[e], yf), -yf1);
+      ry = add_rn(add_rn(area[e], yf), -yf1);  // ra_y (fv_tracer2d.F90:517-521)
+      if (!p.exact) ry = T(1) / ry;
     }
     if (i >= 1 && i <= n) my = mul_rn(myp[(long)(j - 1) * n + (i - 1)], frac);
   }
@@ -227,13 +243,14 @@ template <class T> struct A5View {
   const T* ss;
 };
 #define A5P(v, f, k) ((v).sp[((f) * A5_R + (k)) * A5_GW])
-#define A5S(v, f, k) ((v).ss[((f) * A5_R + (k)) * A5_GW])
+#define A5S(v, f, k) ((v).ss[(f) * A5Stage<T>::SFIELD + (k) * A5Stage<T>::SW])
 #define A5XROW(s, k) ((s).smt + (k) * A5_XP)
 
-template <class T> FV3T_HD A5View<T> a5_view(const void* stage, int gtid) {
+// xs = plane column of the group's thread 0 (strip * A5_W)
+template <class T> FV3T_HD A5View<T> a5_view(const void* stage, int gtid, int xs) {
   A5View<T> v;
   v.sp = reinterpret_cast<const Pair<T>*>(stage) + gtid;
-  v.ss = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(stage) + A5Stage<T>::PAIR_BYTES) + gtid;
+  v.ss = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(stage) + A5Stage<T>::PAIR_BYTES) + gtid + A5Stage<T>::shift(xs);
   return v;
 }
 
@@ -308,7 +325,9 @@ FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3T
 // Dependencies inside a step: 1 -> 2 -> 3 -> 4 through the exchange rows.  Phases 1 and 4 (y direction, register-resident
 // windows) never touch what phases 2 and 3 (x direction, shared-memory rows) write in the same interval, which is what the
 // software-pipelined schedule of adv5_block uses.
-template <class T, int OI, int OO, int PH, bool YE>
+// EX selects the reference's own operation order (divisions by ra_x / ra_y / dp2, no shared reciprocals); instantiated in a
+// translation unit built with -fmad=false it is bit-identical to the FMA-free oracle (and to the strict k_advect2).
+template <class T, int OI, int OO, int PH, bool YE, bool EX = false>
 FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
   const int nd = c.nd;
   const int cc = r - 2;
@@ -320,7 +339,13 @@ FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const T q_o = s.yin.template q_cm1<PH>();
   const T fy2_c = s.yin.template push<PH, YE>(cc, qy, y2.a, c.npx, p.lim_fac, met_y, s.qys + A5V_EIN * A5_GW, A5_GW);
   const T Fy_c = y2.b * fy2_c;
-  const T qi = (q_o * A5S(v, A5_AO, PH) + s.Fy_prev - Fy_c) * A5S(v, A5_RY, PH);  // only rows o = 1..n are consumed
+  T qi;  // only rows o = 1..n are consumed
+  if (EX) {
+    const T ray = A5S(v, A5_RY, PH);  // zero outside rows 1..n: keep the quotient finite there
+    qi = (q_o * A5S(v, A5_AO, PH) + s.Fy_prev - Fy_c) / (ray != T(0) ? ray : T(1));
+  } else {
+    qi = (q_o * A5S(v, A5_AO, PH) + s.Fy_prev - Fy_c) * A5S(v, A5_RY, PH);
+  }
   s.Fy_prev = Fy_c;
   s.qys[(A5V_FY2 + (PH & 1)) * A5_GW] = fy2_c;  // phase 4 of this step runs after phase 1 of the next one
   s.qys[(A5V_QO + (PH & 1)) * A5_GW] = q_o;
@@ -344,7 +369,7 @@ FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, c.npx, qb, dxa_o);
 }
 
-template <class T, int OI, int OO, int PH, bool XE>
+template <class T, int OI, int OO, int PH, bool XE, bool EX = false>
 FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
@@ -362,11 +387,12 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, c.npx, p.lim_fac, qa, aa, dxa_r);
   A5XROW(s, A5X_SF1)[0] = x2r.b * fx2;
   const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, c.npx, p.lim_fac, qb, ab, dxa_o);
-  A5XROW(s, A5X_SFT)[0] = (fxo + s.qys[(A5V_FX2 + ((PH + 1) & 3)) * A5_GW]) * A5S(v, A5_MFX, PH);  // fx2 of row r-3, stored three row steps ago
+  const T fx2o = s.qys[(A5V_FX2 + ((PH + 1) & 3)) * A5_GW];  // fx2 of row r-3, stored three row steps ago
+  A5XROW(s, A5X_SFT)[0] = EX ? T(0.5) * (fxo + fx2o) * A5S(v, A5_MFX, PH) : (fxo + fx2o) * A5S(v, A5_MFX, PH);
   s.qys[(A5V_FX2 + PH) * A5_GW] = fx2;
 }
 
-template <class T, int OI, int OO, int PH, bool YE>
+template <class T, int OI, int OO, int PH, bool YE, bool EX = false>
 FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
   const int n = c.n, nd = c.nd;
   const int cc = r - 2, o = r - 3;
@@ -376,11 +402,22 @@ FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const T* sft = A5XROW(s, A5X_SFT);
   const T qx = A5XROW(s, A5X_Q + PH)[0];
   const T q_o = s.qys[(A5V_QO + (PH & 1)) * A5_GW];
-  const T qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) * A5S(v, A5_RX, PH);
+  T qj;
+  if (EX) {
+    const T rax = A5S(v, A5_RX, PH);
+    qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) / (rax != T(0) ? rax : T(1));
+  } else {
+    qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) * A5S(v, A5_RX, PH);
+  }
   const T fyo_c = s.you.template push<PH, YE>(cc, qj, A5P(v, A5_Y2, PH).a, c.npx, p.lim_fac, met_y, s.qys + A5V_EOU * A5_GW, A5_GW);
-  const T fys_c = (fyo_c + s.qys[(A5V_FY2 + (PH & 1)) * A5_GW]) * A5S(v, A5_MFY, PH);  // mfy is zero outside the faces 1..n+1
+  const T fy2c = s.qys[(A5V_FY2 + (PH & 1)) * A5_GW];
+  const T fys_c = EX ? T(0.5) * (fyo_c + fy2c) * A5S(v, A5_MFY, PH) : (fyo_c + fy2c) * A5S(v, A5_MFY, PH);  // mfy: zero outside faces 1..n+1
   const Pair<T> ab = A5P(v, A5_CAB, PH);
-  const T qnew = q_o * ab.a + (sft[0] - sft[1] + s.fys_prev - fys_c) * ab.b;
+  T qnew;
+  if (EX)  // {dp1, dp2}: (q dp1 + (fx(i) - fx(i+1) + fy(j) - fy(j+1)) rarea) / dp2, fv_tracer2d.F90:538-542
+    qnew = (q_o * ab.a + (sft[0] - sft[1] + s.fys_prev - fys_c) * A5S(v, A5_RA, PH)) / (ab.b != T(0) ? ab.b : T(1));
+  else
+    qnew = q_o * ab.a + (sft[0] - sft[1] + s.fys_prev - fys_c) * ab.b;
   const bool o_ok = !YE || (o >= 1 && o <= n);
   if (o_ok && t.cell) s.qo[(o + 2) * nd] = qnew;
   s.fys_prev = fys_c;
@@ -406,6 +443,7 @@ template <class T> FV3T_HD void a5_box_rows(int b, int* row_of /*[A5_NPAIR + A5_
   row_of[A5_NPAIR + A5_MFY] = r0;
   row_of[A5_NPAIR + A5_AR] = r0 + 2;
   row_of[A5_NPAIR + A5_AO] = r0 - 1;
+  row_of[A5_NPAIR + A5_RA] = r0 - 1;
 }
 
 #ifdef __CUDACC__
@@ -455,7 +493,7 @@ template <bool ONEG> __device__ __forceinline__ void a5_group_sync(int g) {
 // (phases 1-2-3-4 in sequence, three barriers) spent 2.6 of 9.4 stall cycles per issued instruction waiting on fixed-latency
 // FP64 dependencies and 0.8 at barriers (profiles/r02_advect5_v1_ncu.txt).  vp / v / vn: staged boxes of the previous, this and
 // the next block (phase 4 of step r0-1 reads the previous box, phase 1 of step r0+4 the next one).
-template <class T, int OI, int OO, bool YE, bool XE, bool ONEG>
+template <class T, int OI, int OO, bool YE, bool XE, bool ONEG, bool EX>
 __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
                                            const A5View<T>& vp, const A5View<T>& v, const unsigned char* next_stage, uint64_t* full_next,
                                            unsigned par_next, uint64_t* empty_prev, int r0, int g, int gtid) {
@@ -463,49 +501,49 @@ __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta
   adv5_issue_q<T, OI, OO, 2, YE>(c, s, t, r0 + 2);
   async_wait_pending<1>();  // q of row r0+1 has landed (r0 landed one step ago)
   adv5_phase2<T, OI, OO, 0, XE>(p, c, s, t, r0);
-  if (!YE || r0 > -2) adv5_phase4<T, OI, OO, 3, YE>(p, c, s, t, vp, r0 - 1);
+  if (!YE || r0 > -2) adv5_phase4<T, OI, OO, 3, YE, EX>(p, c, s, t, vp, r0 - 1);
   if (empty_prev) {  // the previous box is free for the producer
     __syncwarp();
     if ((gtid & 31) == 0) a5_mbar_arrive(empty_prev);
   }
   a5_group_sync<ONEG>(g);
-  adv5_phase3<T, OI, OO, 0, XE>(p, c, s, t, v, r0);
-  adv5_phase1<T, OI, OO, 1, YE>(p, c, s, t, v, r0 + 1);
+  adv5_phase3<T, OI, OO, 0, XE, EX>(p, c, s, t, v, r0);
+  adv5_phase1<T, OI, OO, 1, YE, EX>(p, c, s, t, v, r0 + 1);
   a5_group_sync<ONEG>(g);
   // ---- step r0+1 (PH 1)
   adv5_issue_q<T, OI, OO, 3, YE>(c, s, t, r0 + 3);
   async_wait_pending<1>();
   adv5_phase2<T, OI, OO, 1, XE>(p, c, s, t, r0 + 1);
-  adv5_phase4<T, OI, OO, 0, YE>(p, c, s, t, v, r0);
+  adv5_phase4<T, OI, OO, 0, YE, EX>(p, c, s, t, v, r0);
   a5_group_sync<ONEG>(g);
-  adv5_phase3<T, OI, OO, 1, XE>(p, c, s, t, v, r0 + 1);
-  adv5_phase1<T, OI, OO, 2, YE>(p, c, s, t, v, r0 + 2);
+  adv5_phase3<T, OI, OO, 1, XE, EX>(p, c, s, t, v, r0 + 1);
+  adv5_phase1<T, OI, OO, 2, YE, EX>(p, c, s, t, v, r0 + 2);
   a5_group_sync<ONEG>(g);
   // ---- step r0+2 (PH 2)
   adv5_issue_q<T, OI, OO, 0, YE>(c, s, t, r0 + 4);
   async_wait_pending<1>();
   adv5_phase2<T, OI, OO, 2, XE>(p, c, s, t, r0 + 2);
-  adv5_phase4<T, OI, OO, 1, YE>(p, c, s, t, v, r0 + 1);
+  adv5_phase4<T, OI, OO, 1, YE, EX>(p, c, s, t, v, r0 + 1);
   a5_group_sync<ONEG>(g);
-  adv5_phase3<T, OI, OO, 2, XE>(p, c, s, t, v, r0 + 2);
-  adv5_phase1<T, OI, OO, 3, YE>(p, c, s, t, v, r0 + 3);
+  adv5_phase3<T, OI, OO, 2, XE, EX>(p, c, s, t, v, r0 + 2);
+  adv5_phase1<T, OI, OO, 3, YE, EX>(p, c, s, t, v, r0 + 3);
   a5_group_sync<ONEG>(g);
   // ---- step r0+3 (PH 3)
   adv5_issue_q<T, OI, OO, 1, YE>(c, s, t, r0 + 5);
   async_wait_pending<1>();
   adv5_phase2<T, OI, OO, 3, XE>(p, c, s, t, r0 + 3);
-  adv5_phase4<T, OI, OO, 2, YE>(p, c, s, t, v, r0 + 2);
+  adv5_phase4<T, OI, OO, 2, YE, EX>(p, c, s, t, v, r0 + 2);
   a5_group_sync<ONEG>(g);
-  adv5_phase3<T, OI, OO, 3, XE>(p, c, s, t, v, r0 + 3);
+  adv5_phase3<T, OI, OO, 3, XE, EX>(p, c, s, t, v, r0 + 3);
   if (full_next) {
     a5_mbar_wait(full_next, par_next);
-    const A5View<T> vn = a5_view<T>(next_stage, gtid);
-    adv5_phase1<T, OI, OO, 0, YE>(p, c, s, t, vn, r0 + 4);
+    const A5View<T> vn = a5_view<T>(next_stage, gtid, c.i0 - 1);
+    adv5_phase1<T, OI, OO, 0, YE, EX>(p, c, s, t, vn, r0 + 4);
   }
   a5_group_sync<ONEG>(g);
 }
 
-template <class T, int OI, int OO, int NTHR, int MINB>
+template <class T, int OI, int OO, int NTHR, int MINB, bool EX = false>
 __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ Adv5Params<T> p, const __grid_constant__ Adv5Maps maps) {
   extern __shared__ __align__(128) unsigned char smem5[];
   using S = A5Stage<T>;
@@ -536,21 +574,23 @@ __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ 
       int st = 0, wrap = 0;
       for (int b = 0; b < nblocks; ++b) {
         if (b >= A5_NS) a5_mbar_wait(&empty[st], (wrap - 1) & 1);
-        a5_mbar_expect_tx(&full[st], S::BYTES);
+        a5_mbar_expect_tx(&full[st], S::TX_BYTES);
         unsigned char* base = smem5 + st * S::BYTES;
-        constexpr int PB = A5_R * A5_GW * 2 * (int)sizeof(T), SB = A5_R * A5_GW * (int)sizeof(T);
+        constexpr int PB = A5_R * A5_GW * 2 * (int)sizeof(T), SB = S::SBYTES;
+        const int xq = xs - S::shift(xs);  // 16-byte aligned start of the scalar boxes
         const int r0 = -2 + A5_R * b;
         a5_tma_3d(base + A5_XR * PB, &maps.x2, 2 * xs, r0 + 2, levc, &full[st]);
         a5_tma_3d(base + A5_XO * PB, &maps.x2, 2 * xs, r0 - 1, levc, &full[st]);
         a5_tma_3d(base + A5_Y2 * PB, &maps.y2, 2 * xs, r0, levc, &full[st]);
         a5_tma_3d(base + A5_CAB * PB, &maps.cab, 2 * xs, r0 - 1, levc, &full[st]);
         unsigned char* sb = base + S::PAIR_BYTES;
-        a5_tma_3d(sb + A5_RX * SB, &maps.rx, xs, r0 + 2, levc, &full[st]);
-        a5_tma_3d(sb + A5_MFX * SB, &maps.mfx, xs, r0 - 1, levc, &full[st]);
-        a5_tma_3d(sb + A5_RY * SB, &maps.ry, xs, r0 - 1, levc, &full[st]);
-        a5_tma_3d(sb + A5_MFY * SB, &maps.mfy, xs, r0, levc, &full[st]);
-        a5_tma_3d(sb + A5_AR * SB, &maps.area, xs, r0 + 2, tile, &full[st]);
-        a5_tma_3d(sb + A5_AO * SB, &maps.area, xs, r0 - 1, tile, &full[st]);
+        a5_tma_3d(sb + A5_RX * SB, &maps.rx, xq, r0 + 2, levc, &full[st]);
+        a5_tma_3d(sb + A5_MFX * SB, &maps.mfx, xq, r0 - 1, levc, &full[st]);
+        a5_tma_3d(sb + A5_RY * SB, &maps.ry, xq, r0 - 1, levc, &full[st]);
+        a5_tma_3d(sb + A5_MFY * SB, &maps.mfy, xq, r0, levc, &full[st]);
+        a5_tma_3d(sb + A5_AR * SB, &maps.area, xq, r0 + 2, tile, &full[st]);
+        a5_tma_3d(sb + A5_AO * SB, &maps.area, xq, r0 - 1, tile, &full[st]);
+        a5_tma_3d(sb + A5_RA * SB, &maps.rarea, xq, r0 - 1, tile, &full[st]);
         if (++st == A5_NS) {
           st = 0;
           ++wrap;
@@ -574,8 +614,9 @@ __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ 
   adv5_issue_q<T, OI, OO, 1, true>(c, s, t, -1);
   async_wait_all();
   a5_mbar_wait(&full[0], 0);
-  A5View<T> v = a5_view<T>(smem5, gtid), vp = v;
-  adv5_phase1<T, OI, OO, 0, true>(p, c, s, t, v, -2);
+  const int xs = strip * A5_W;
+  A5View<T> v = a5_view<T>(smem5, gtid, xs), vp = v;
+  adv5_phase1<T, OI, OO, 0, true, EX>(p, c, s, t, v, -2);
   a5_group_sync<ONEG>(g);
   int st = 0, wrap = 0;
   for (int b = 0; b < nblocks; ++b) {
@@ -591,14 +632,14 @@ __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ 
     uint64_t* empty_prev = b > 0 ? &empty[sp] : nullptr;
     if (a5_block_interior(r0, n)) {
       if (c.xedge)
-        adv5_block<T, OI, OO, false, true, ONEG>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
+        adv5_block<T, OI, OO, false, true, ONEG, EX>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
       else
-        adv5_block<T, OI, OO, false, false, ONEG>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
+        adv5_block<T, OI, OO, false, false, ONEG, EX>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
     } else {
-      adv5_block<T, OI, OO, true, true, ONEG>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
+      adv5_block<T, OI, OO, true, true, ONEG, EX>(p, c, s, t, vp, v, next_stage, full_next, wn & 1, empty_prev, r0, g, gtid);
     }
     vp = v;
-    v = a5_view<T>(next_stage, gtid);
+    v = a5_view<T>(next_stage, gtid, xs);
     st = sn;
     wrap = wn;
   }

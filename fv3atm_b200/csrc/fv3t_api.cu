@@ -133,11 +133,12 @@ template <class T> struct Impl {
   T *rrx = nullptr, *rry = nullptr;
   // multi-tracer TMA-staged advection (fv3t_advect5.cuh): padded-pitch scratch planes + their tensor maps
   fv3t::Pair<T>*X5 = nullptr, *Y5 = nullptr, *C5 = nullptr;
-  T *RX5 = nullptr, *RY5 = nullptr, *MX5 = nullptr, *MY5 = nullptr, *AREA5 = nullptr;
+  T *RX5 = nullptr, *RY5 = nullptr, *MX5 = nullptr, *MY5 = nullptr, *AREA5 = nullptr, *RAREA5 = nullptr;
   fv3t::Adv5Maps maps5;
   bool maps5_ok = false;
   bool use5 = true;            // FV3T_ADV5=0 keeps the per-tracer k_advect4
   bool call5 = false;          // the current tracer_2d call runs k_advect5
+  bool exact5 = false;         // ... its exact-arithmetic instantiation (schemes outside fast_hord_ok: bit-identical to the oracle)
   bool scale_pending = false;  // k_advect5 path: the in-place 1/ksplt scaling of cx, cy, mfx, mfy is applied by finish()
   fv3t::Pair<T>* P1 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
   T *GAM = nullptr, *RD1 = nullptr, *R2 = nullptr;
@@ -361,7 +362,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
 template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, coef4, neg4, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
+  void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, RAREA5, coef4, neg4, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -543,8 +544,10 @@ template <class T> int Impl<T>::alloc5() {
   CK(zalloc((void**)&MX5, e * sizeof(T)));
   CK(zalloc((void**)&MY5, e * sizeof(T)));
   CK(zalloc((void**)&AREA5, (size_t)nt * nd * PP * sizeof(T)));
+  CK(zalloc((void**)&RAREA5, (size_t)nt * nd * PP * sizeof(T)));
   CK(fv3t::fast_pad_plane<T>(AREA5, area, nd, PP, nt, stream));
-  ++launches;
+  CK(fv3t::fast_pad_plane<T>(RAREA5, rarea, nd, PP, nt, stream));
+  launches += 2;
   fv3t::Adv5Params<T> p{};
   p.X2 = X5;
   p.Y2 = Y5;
@@ -554,6 +557,7 @@ template <class T> int Impl<T>::alloc5() {
   p.MFX = MX5;
   p.MFY = MY5;
   p.AREA = AREA5;
+  p.RAREA = RAREA5;
   p.n = n;
   p.npz = npz;
   p.ntiles = nt;
@@ -565,13 +569,17 @@ template <class T> int Impl<T>::alloc5() {
 
 template <class T> int Impl<T>::prepare(int hord, bool allow5) {
   call_fast = fast && fv3t::fast_hord_ok(hord);
-  call5 = call_fast && use5 && allow5 && fv3t::adv5_hord_ok(hord);
+  // k_advect5 shares the staged level fields among the tracers of a CTA and takes one CTA per SM: with fewer than four resident
+  // tracers (small tracer groups of a sharded run) the per-tracer CTAs of k_advect4 / k_advect2 keep more warps in flight.
+  // Schemes outside fast_hord_ok run its exact-arithmetic instantiation (FV3T_STRICT=1 keeps everything on k_advect2).
+  call5 = fast && use5 && allow5 && fv3t::adv5_hord_ok(hord) && nq_cur >= 4;
+  exact5 = call5 && !call_fast;
   auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
   if (call5) {
     const int rc = alloc5();
     if (rc) return rc;
     fv3t::Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X5, Y5, C5, RX5, RY5, MX5, MY5,
-                            ksplt_d, n, npz, nt, 0, nt * npz, 1, 1};
+                            ksplt_d, n, npz, nt, 0, nt * npz, 1, 1, exact5 ? 1 : 0};
     kbegin();
     CK(fv3t::fast_prep5<T>(pp, stream));
     kend(KC_SCALE);
@@ -618,7 +626,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     if (!fv3t::adv5_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
     if (it > 1) {  // dp1 <- dp2 of sub-step it-1 (fv_tracer2d.F90:547-553), then dp1/dp2, 0.5*rarea/dp2 of this sub-step
       fv3t::Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X5, Y5, C5, RX5, RY5, MX5, MY5,
-                              ksplt_d, n, npz, nt, 0, nt * npz, it, 0};
+                              ksplt_d, n, npz, nt, 0, nt * npz, it, 0, exact5 ? 1 : 0};
       kbegin();
       CK(fv3t::fast_prep5<T>(pp, stream));
       kend(KC_SCALE);
@@ -634,6 +642,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     p.MFX = MX5;
     p.MFY = MY5;
     p.AREA = AREA5;
+    p.RAREA = RAREA5;
     p.dxa = dxa;
     p.dya = dya;
     p.ksplt = ksplt_d;
@@ -651,7 +660,10 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
       if (rcs) return rcs;
     }
     kbegin();
-    CK(fv3t::fast_advect5<T>(p, maps5, hord, nt * npz, stream));
+    if (exact5)
+      CK(fv3t::exact_advect5<T>(p, maps5, hord, nt * npz, stream));
+    else
+      CK(fv3t::fast_advect5<T>(p, maps5, hord, nt * npz, stream));
     kend(KC_ADVECT);
     return 0;
   }
@@ -1027,6 +1039,7 @@ int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const
       p.MFX = MX5;
       p.MFY = MY5;
       p.AREA = AREA5;
+      p.RAREA = RAREA5;
       p.dxa = dxa;
       p.dya = dya;
       p.ksplt = ksplt_d;

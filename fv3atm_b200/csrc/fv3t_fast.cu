@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cudaTypedefs.h>
 
+#include "fv3t_advect5_launch.cuh"
+
 namespace fv3t {
 
 template <class T> cudaError_t fast_prep3(const Prep3Params<T>& p, cudaStream_t stream) {
@@ -101,7 +103,7 @@ template <class T> static cudaError_t encode_plane_map(CUtensorMap* m, const voi
   if (!enc) return cudaErrorNotSupported;
   const cuuint64_t gdim[3] = {(cuuint64_t)PP * per, (cuuint64_t)nd, (cuuint64_t)planes};
   const cuuint64_t gstr[2] = {(cuuint64_t)PP * per * sizeof(T), (cuuint64_t)PP * per * sizeof(T) * nd};
-  const cuuint32_t box[3] = {(cuuint32_t)(A5_GW * per), (cuuint32_t)A5_R, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)(per == 2 ? A5_GW * 2 : A5Stage<T>::SW), (cuuint32_t)A5_R, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -118,46 +120,18 @@ template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T
   if ((e = encode_plane_map<T>(&m->ry, p.RY, PP, nd, nlev, 1)) != cudaSuccess) return e;
   if ((e = encode_plane_map<T>(&m->mfx, p.MFX, PP, nd, nlev, 1)) != cudaSuccess) return e;
   if ((e = encode_plane_map<T>(&m->mfy, p.MFY, PP, nd, nlev, 1)) != cudaSuccess) return e;
-  return encode_plane_map<T>(&m->area, p.AREA, PP, nd, p.ntiles, 1);
+  if ((e = encode_plane_map<T>(&m->area, p.AREA, PP, nd, p.ntiles, 1)) != cudaSuccess) return e;
+  return encode_plane_map<T>(&m->rarea, p.RAREA, PP, nd, p.ntiles, 1);
 }
 
-template <class T, int OI, int OO, int TGC> static cudaError_t launch5(const Adv5Params<T>& p, const Adv5Maps& m, dim3 grid, cudaStream_t stream) {
-  constexpr int NTHR = 32 + A5_GW * TGC;
-  // the named barriers of the tracer groups take all 16 hardware barriers: one CTA per SM; a one-tracer CTA uses one (two CTAs per SM)
-  constexpr int MINB = TGC == 1 ? 2 : 1;
-  const size_t smem = A5Stage<T>::smem_bytes(p.tg);
-  cudaError_t e = cudaFuncSetAttribute(k_advect5<T, OI, OO, NTHR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_advect5<T, OI, OO, NTHR, MINB><<<grid, 32 + A5_GW * p.tg, smem, stream>>>(p, m);
-  return cudaGetLastError();
-}
-template <class T, int OI, int OO> static cudaError_t launch5_ord(Adv5Params<T>& p, const Adv5Maps& m, int nlev, cudaStream_t stream) {
-  // tracers per CTA: every tracer group of a CTA shares the staged level fields.  FV3T_ADV_TG caps it (tuning knob).
-  static const int cap_env = getenv("FV3T_ADV_TG") ? atoi(getenv("FV3T_ADV_TG")) : A5_MAXTG;
-  const int cap = cap_env < 1 ? 1 : (cap_env > A5_MAXTG ? A5_MAXTG : cap_env);
-  const int chunks = (p.nql + cap - 1) / cap;
-  p.tg = (p.nql + chunks - 1) / chunks;
-  const int strips = (p.n + A5_W - 1) / A5_W;
-  dim3 grid(strips, nlev, chunks);
-  if (p.tg == 1) return launch5<T, OI, OO, 1>(p, m, grid, stream);
-  if (p.tg > 5) return launch5<T, OI, OO, 9>(p, m, grid, stream);
-  return launch5<T, OI, OO, 5>(p, m, grid, stream);
-}
 template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
   switch (hord) {
-    case 8: return launch5_ord<T, 8, 8>(p, m, nlev, stream);
-    case 10: return launch5_ord<T, 8, 10>(p, m, nlev, stream);
-#ifndef FV3T_A5_DEV
-    case 9: return launch5_ord<T, 9, 9>(p, m, nlev, stream);
-    case 11: return launch5_ord<T, 11, 11>(p, m, nlev, stream);
-    case 12: return launch5_ord<T, 12, 12>(p, m, nlev, stream);
-    case 13: return launch5_ord<T, 13, 13>(p, m, nlev, stream);
-    case 2: return launch5_ord<T, 2, 2>(p, m, nlev, stream);
-#endif
+    case 8: return launch5_ord<T, 8, 8, false>(p, m, nlev, stream);
+    case 11: return launch5_ord<T, 11, 11, false>(p, m, nlev, stream);
+    case 2: return launch5_ord<T, 2, 2, false>(p, m, nlev, stream);
     default: return cudaErrorInvalidValue;
   }
 }
-
 
 // ---- k_remap4 ---------------------------------------------------------------------------------------------------------------
 template <class T> size_t remap4_coef_bytes(int n, int ntiles) { return (size_t)ntiles * n * r4_groups_per_row(n) * R4Block<T>::BYTES; }

@@ -13,7 +13,9 @@
 namespace fv3t {
 
 // hord values whose limiter is a continuous function of its inputs: only these may use the fast path
-inline bool fast_hord_ok(int hord) { return hord == 8 || hord == 9 || hord == 11 || hord == 12 || hord == 13 || hord == 2; }
+// (9, 12, 13 carry the positive-definite constraint that zeroes BOTH edge perturbations when the parabola's minimum crosses
+// zero -- a jump: measured 3.8e-3 on the sparse random tracer in fp32 at C384 with four sub-steps -- so they are not in the set)
+inline bool fast_hord_ok(int hord) { return hord == 8 || hord == 11 || hord == 2; }
 
 // abs(kord) values whose limiter decisions depend only on the INPUT cell means (not on computed interface values): only
 // these may use the fast remap (kord 10, 11, 15, 16 compare computed quantities that are exactly equal on flat data)
@@ -29,8 +31,8 @@ template <class T> cudaError_t fast_cab3(const Cab3Params<T>& p, int ntiles, cud
 template <class T> cudaError_t fast_advect3(Adv3Params<T> p, int hord, int NT, cudaStream_t stream);
 
 // ---- multi-tracer TMA-staged advection (fv3t_advect5.cuh) ----
-// schemes instantiated for k_advect5 (a subset of fast_hord_ok keeps the build time bounded)
-inline bool adv5_hord_ok(int hord) { return hord == 8 || hord == 10 || hord == 9 || hord == 12 || hord == 13 || hord == 11 || hord == 2; }
+// every scheme of xppm / yppm has an exact-arithmetic instantiation of k_advect5 (fv3t_exact.cu); fast_hord_ok also a fast one
+inline bool adv5_hord_ok(int hord) { return (hord >= 1 && hord <= 13) || hord == -5; }
 template <class T> cudaError_t fast_prep5(const Prep5Params<T>& p, cudaStream_t stream);
 template <class T> cudaError_t fast_pad_plane(T* dst, const T* src, int nd, int PP, int ntiles, cudaStream_t stream);
 // tensor maps of the scratch planes (nlev levels resident) and of the padded area array; returns cudaErrorNotSupported
@@ -38,6 +40,8 @@ template <class T> cudaError_t fast_pad_plane(T* dst, const T* src, int nd, int 
 template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T>& p, int nlev);
 // p.tg is chosen by the launcher; nlev = levels of the resident chunk (grid.y)
 template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
+// the reference's operation order, bit-identical to the FMA-free oracle (fv3t_exact.cu, -fmad=false); needs k_prep5 with exact = 1
+template <class T> cudaError_t exact_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
 
 // ---- lanes-over-levels remap (fv3t_remap4.cuh): km <= 127, mapn_tracer form, uniform abs(kord) in fast_kord_ok ----
 template <class T> size_t remap4_coef_bytes(int n, int ntiles);

@@ -276,6 +276,10 @@ def bench_face_sharded(args, rank: int, world: int, local_rank: int, prefer: str
             nsplt = one()
         stream.synchronize()
         dist.barrier()
+        sampler = None
+        if rank == 0 and getattr(args, "clock_sampler", None):
+            sampler = args.clock_sampler(local_rank)
+            sampler.start()
         l0 = ctx.kernel_launches()
         ctx.timer_start()
         for _ in range(args.steps):
@@ -284,10 +288,87 @@ def bench_face_sharded(args, rank: int, world: int, local_rank: int, prefer: str
         launches = ctx.kernel_launches() - l0
         stream.synchronize()
         dist.barrier()
+        clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     updates = 6 * n * n * npz * nq
+    cells_rank = len(tiles) * n * n * npz
+
+    # ---- per-kernel roofline of rank 0's share (separate pass with per-kernel event timing, not part of the timed region)
+    roof = None
+    with torch.cuda.stream(stream):
+        ctx.profile_enable(True)
+        for _ in range(2):
+            one()
+        adv_ms, adv_n = ctx.profile_get("advect")
+        rm_ms, rm_n = ctx.profile_get("remap")
+        halo_ms, _ = ctx.profile_get("halo")
+        oth = sum(ctx.profile_get(k)[0] for k in ("cmax", "scale"))
+        ctx.profile_enable(False)
+        stream.synchronize()
+    dist.barrier()
+    if rank == 0:
+        import json as _json
+        import os as _os
+        peak, which = 6650.0, "fallback"
+        try:
+            peak = float(_json.load(open(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+            which = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+        adv_bytes = cells_rank * (2 * w * nq_local + 5 * w)
+        rm_bytes = cells_rank * (2 * w * nq_local + 2 * w)
+        adv_avg, rm_avg = adv_ms / max(adv_n, 1), rm_ms / max(rm_n, 1)
+        dom_adv = adv_ms >= rm_ms
+        a_bytes, a_ms = (adv_bytes, adv_avg) if dom_adv else (rm_bytes, rm_avg)
+        ach = a_bytes / (a_ms * 1e-3) / 1e9
+        B = 2 * w * 2 + w * 7 / nq_local
+        roof = {"bound": "hbm", "kernel": ("k_advect5" if nq_local >= 4 else "k_advect4") if dom_adv else "k_remap3", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": which, "bytes_per_launch": a_bytes, "avg_launch_ms": a_ms,
+                "rank0_ms_per_step": {"advect": adv_ms / 2, "remap": rm_ms / 2, "halo pack/unpack kernels": halo_ms / 2, "prep/coef/cmax": oth / 2},
+                "step_frac_of_roofline_per_gpu": (updates / world / (ms_max / args.steps * 1e-3)) * B / (peak * 1e9)}
+
+    # ---- end to end: every rank's share of the inputs starts in pinned host memory and its results end there
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        from .devarray import field_shape
+        fields_in = ["q", "dp1", "mfx", "mfy", "cx", "cy", "pe"]
+        host = {f: torch.empty(field_shape(ctx, f, nq_local), dtype=step.tdt, pin_memory=True) for f in fields_in + ["delp"]}
+        with torch.cuda.stream(stream):
+            sd.fill_context(ctx, grid, nq_local, courant=args.courant, seed=20260101, device=local_rank, q_first=q_first)
+            for f in fields_in:
+                ctx.download_ptr(f, host[f].data_ptr(), nq_local)
+            stream.synchronize()
+
+            def e2e_step():
+                for f in fields_in:
+                    ctx.upload_ptr(f, host[f].data_ptr(), nq_local)
+                ctx.set_vertical(ak_h, bk_h, ptop_h)
+                one()
+                ctx.download_ptr("q", host["q"].data_ptr(), nq_local)
+                ctx.download_ptr("delp", host["delp"].data_ptr(), nq_local)
+
+            ak_h, bk_h, ptop_h = sd.hybrid(npz)
+            e2e_step()
+            stream.synchronize()
+            dist.barrier()
+            import time as _time
+            t0 = _time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            stream.synchronize()
+            dist.barrier()
+            wall = (_time.perf_counter() - t0) * 1e3
+        et = torch.tensor([wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([sum(host[f].numel() * w for f in fields_in)], dtype=torch.float64, device=dev)
+        d2h = torch.tensor([(host["q"].numel() + host["delp"].numel()) * w], dtype=torch.float64, device=dev)
+        dist.all_reduce(h2d)
+        dist.all_reduce(d2h)
+        e2e = {"value": updates * args.e2e_steps / (float(et.item()) * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d.item()),
+               "d2h_bytes_per_step": int(d2h.item()), "steps": args.e2e_steps, "ms_per_step": float(et.item()) / args.e2e_steps}
+        del host
     if rank == 0:
         strip_bytes = 3 * n * npz * nq_local * w
         sends, _ = strip_schedule(layout, rank)
@@ -297,12 +378,14 @@ def bench_face_sharded(args, rank: int, world: int, local_rank: int, prefer: str
                 "data": "synthetic",
                 "config": {"workload": f"C{n} L{npz}, {nq} tracers in total, {args.dtype}, hord_tr={args.hord}, kord_tr={args.kord}, fill, "
                                        f"tracer_2d + tracer remap",
-                           "parallelism": f"{F} face groups x {G} tracer groups; rank 0: tiles {list(tiles)}, {nq_local} tracers",
-                           "halo": (f"{len(sends)} NCCL send/recv strips of {strip_bytes} B per rank and sub-step + all-reduce(max) of cmax"
-                                    if F > 1 else "none: tracer groups only, winds / mass fluxes / delp replicated (no data-path collective)"),
+                           "parallelism": f"ONE problem split over {F} face groups x {G} tracer groups; rank 0: tiles {list(tiles)}, {nq_local} tracers",
+                           "halo": (f"{len(sends)} NCCL send/recv strips of {strip_bytes} B per rank and sub-step ({len(sends) * strip_bytes} B sent per rank) "
+                                    f"+ all-reduce(max) of cmax" if F > 1 else
+                                    "none: tracer groups only, winds / mass fluxes / delp replicated (no data-path collective)"),
+                           "halo_bytes_sent_per_rank_and_substep": len(sends) * strip_bytes if F > 1 else 0,
                            "nsplt": int(nsplt), "updates_per_step": updates,
                            "l2": "inputs (GBs per rank) far exceed the 126 MB L2; no flush needed"},
-                "gpu_launches": int(launches), "e2e": None, "roofline": None, "cpu_baseline": None, "clocks": None}
+                "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": None, "clocks": clocks}
         print(json.dumps(line))
     ctx.close()
     dist.destroy_process_group()

@@ -28,22 +28,23 @@ template <class T> static void fill_stage(const Adv5Params<T>& p, int strip, int
         if (row >= 0 && row < nd && col >= 0 && col < PP) v = psrc[f][((long)levc * nd + row) * PP + col];
         pd[(f * A5_R + k) * A5_GW + x] = v;
       }
-  const T* ssrc[A5_NSC] = {p.RX, p.MFX, p.RY, p.MFY, p.AREA, p.AREA};
+  const T* ssrc[A5_NSC] = {p.RX, p.MFX, p.RY, p.MFY, p.AREA, p.AREA, p.RAREA};
   T* sd = reinterpret_cast<T*>(stage + A5Stage<T>::PAIR_BYTES);
+  const int xq = xs - A5Stage<T>::shift(xs);
   for (int f = 0; f < A5_NSC; ++f)
     for (int k = 0; k < A5_R; ++k)
-      for (int x = 0; x < A5_GW; ++x) {
-        const int row = rows[A5_NPAIR + f] + k, col = xs + x;
+      for (int x = 0; x < A5Stage<T>::SW; ++x) {
+        const int row = rows[A5_NPAIR + f] + k, col = xq + x;
         const long plane_idx = (f >= A5_AR) ? tile : levc;
         T v = T(0);
         if (row >= 0 && row < nd && col >= 0 && col < PP) v = ssrc[f][(plane_idx * nd + row) * PP + col];
-        sd[(f * A5_R + k) * A5_GW + x] = v;
+        sd[f * A5Stage<T>::SFIELD + k * A5Stage<T>::SW + x] = v;
       }
 }
 
 // one block of four row steps in the product's two-interval schedule (adv5_block): interval 1 = phase 2 of step s + phase 4 of
 // step s-1, interval 2 = phase 3 of step s + phase 1 of step s+1; a barrier (= end of a loop over the threads) after each
-template <class T, int OI, int OO> struct Sim {
+template <class T, int OI, int OO, bool EX> struct Sim {
   const Adv5Params<T>& p;
   const Adv5Cta& c;
   std::vector<Adv5State<T, OI, OO>>& st;
@@ -54,11 +55,11 @@ template <class T, int OI, int OO> struct Sim {
     for (int tid = 0; tid < A5_GW; ++tid) {
       adv5_issue_q<T, OI, OO, PHQ, YE>(c, st[tid], th[tid], r + 2);
       adv5_phase2<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], r);
-      if (do4) adv5_phase4<T, OI, OO, PH4, YE>(p, c, st[tid], th[tid], a5_view<T>(stage4, tid), r - 1);
+      if (do4) adv5_phase4<T, OI, OO, PH4, YE, EX>(p, c, st[tid], th[tid], a5_view<T>(stage4, tid, c.i0 - 1), r - 1);
     }
     for (int tid = 0; tid < A5_GW; ++tid) {
-      adv5_phase3<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], a5_view<T>(stage, tid), r);
-      if (do1) adv5_phase1<T, OI, OO, PH1, YE>(p, c, st[tid], th[tid], a5_view<T>(stage1, tid), r + 1);
+      adv5_phase3<T, OI, OO, PH, XE, EX>(p, c, st[tid], th[tid], a5_view<T>(stage, tid, c.i0 - 1), r);
+      if (do1) adv5_phase1<T, OI, OO, PH1, YE, EX>(p, c, st[tid], th[tid], a5_view<T>(stage1, tid, c.i0 - 1), r + 1);
     }
   }
   template <bool YE, bool XE> void block(const unsigned char* sp, const unsigned char* sc, const unsigned char* sn, int r0) {
@@ -69,7 +70,7 @@ template <class T, int OI, int OO> struct Sim {
   }
 };
 
-template <class T, int OI, int OO> static void run_substep(const Adv5Params<T>& p) {
+template <class T, int OI, int OO, bool EX> static void run_substep(const Adv5Params<T>& p) {
   const int n = p.n;
   const int strips = (n + A5_W - 1) / A5_W;
   const int nblocks = a5_nblocks(n);
@@ -84,14 +85,14 @@ template <class T, int OI, int OO> static void run_substep(const Adv5Params<T>& 
       for (int iq = p.iq0; iq < p.iq0 + p.nql; ++iq) {
         Adv5Cta c;
         if (!adv5_make_cta<T>(p, strip, levc, iq, c)) continue;
-        Sim<T, OI, OO> sim{p, c, st, th};
+        Sim<T, OI, OO, EX> sim{p, c, st, th};
         fill_stage<T>(p, strip, levc, 0, sg);
         for (int tid = 0; tid < A5_GW; ++tid) {
           th[tid] = adv5_thread(c, tid);
           adv5_init<T, OI, OO>(p, c, th[tid], gs, st[tid]);
           adv5_issue_q<T, OI, OO, 0, true>(c, st[tid], th[tid], -2);
           adv5_issue_q<T, OI, OO, 1, true>(c, st[tid], th[tid], -1);
-          adv5_phase1<T, OI, OO, 0, true>(p, c, st[tid], th[tid], a5_view<T>(sg, tid), -2);
+          adv5_phase1<T, OI, OO, 0, true, EX>(p, c, st[tid], th[tid], a5_view<T>(sg, tid, c.i0 - 1), -2);
         }
         for (int b = 0; b < nblocks; ++b) {
           const int r0 = -2 + A5_R * b;
@@ -114,15 +115,26 @@ template <class T, int OI, int OO> static void run_substep(const Adv5Params<T>& 
       }
 }
 
-template <class T> static int dispatch(const Adv5Params<T>& p, int hord) {
+// the instantiations the product builds: fast for fv3t::fast_hord_ok, exact for every scheme
+template <class T, bool EX> static int dispatch(const Adv5Params<T>& p, int hord) {
   switch (hord) {
-    case 8: run_substep<T, 8, 8>(p); break;
-    case 10: run_substep<T, 8, 10>(p); break;
-    case 9: run_substep<T, 9, 9>(p); break;
-    case 11: run_substep<T, 11, 11>(p); break;
-    case 12: run_substep<T, 12, 12>(p); break;
-    case 13: run_substep<T, 13, 13>(p); break;
-    case 2: run_substep<T, 2, 2>(p); break;
+    case 8: run_substep<T, 8, 8, EX>(p); return 0;
+    case 11: run_substep<T, 11, 11, EX>(p); return 0;
+    case 2: run_substep<T, 2, 2, EX>(p); return 0;
+  }
+  if (!EX) return 1;
+  switch (hord) {
+    case 10: run_substep<T, 8, 10, true>(p); break;
+    case 9: run_substep<T, 9, 9, true>(p); break;
+    case 12: run_substep<T, 12, 12, true>(p); break;
+    case 13: run_substep<T, 13, 13, true>(p); break;
+    case 7: run_substep<T, 7, 7, true>(p); break;
+    case 5: run_substep<T, 5, 5, true>(p); break;
+    case -5: run_substep<T, -5, -5, true>(p); break;
+    case 6: run_substep<T, 6, 6, true>(p); break;
+    case 1: run_substep<T, 1, 1, true>(p); break;
+    case 3: run_substep<T, 3, 3, true>(p); break;
+    case 4: run_substep<T, 4, 4, true>(p); break;
     default: return 1;
   }
   return 0;
@@ -132,20 +144,23 @@ template <class T> static int dispatch(const Adv5Params<T>& p, int hord) {
 template <class T>
 static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area, const T* rarea,
                          const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, const int64_t* halo_dst,
-                         const int64_t* halo_src, int64_t halo_len, int hord, T lim_fac, int nsplt, const int* ksplt) {
+                         const int64_t* halo_src, int64_t halo_len, int hord, T lim_fac, int nsplt, const int* ksplt, int exact) {
   const int nt = 6, nd = n + 6, PP = a5_pitch(n);
   const long plane = (long)nd * nd;
   const size_t nlev = (size_t)nt * npz, pe = nlev * nd * PP;
   std::vector<Pair<T>> X2(pe, Pair<T>{T(0), T(0)}), Y2(pe, Pair<T>{T(0), T(0)}), CAB(pe, Pair<T>{T(0), T(0)});
-  std::vector<T> RX(pe, T(0)), RY(pe, T(0)), MX(pe, T(0)), MY(pe, T(0)), AREA((size_t)nt * nd * PP, T(0));
+  std::vector<T> RX(pe, T(0)), RY(pe, T(0)), MX(pe, T(0)), MY(pe, T(0)), AREA((size_t)nt * nd * PP, T(0)), RAREA((size_t)nt * nd * PP, T(0));
   for (int t = 0; t < nt; ++t)
     for (int r = 0; r < nd; ++r)
-      for (int x = 0; x < nd; ++x) AREA[((size_t)t * nd + r) * PP + x] = area[(size_t)t * plane + (size_t)r * nd + x];
+      for (int x = 0; x < nd; ++x) {
+        AREA[((size_t)t * nd + r) * PP + x] = area[(size_t)t * plane + (size_t)r * nd + x];
+        RAREA[((size_t)t * nd + r) * PP + x] = rarea[(size_t)t * plane + (size_t)r * nd + x];
+      }
   std::vector<T> qb((size_t)nt * nq * npz * plane);
   const long tile_stride = plane * npz * nq;
   for (int it = 1; it <= nsplt; ++it) {
     Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X2.data(), Y2.data(), CAB.data(), RX.data(),
-                      RY.data(), MX.data(), MY.data(), ksplt, n, npz, nt, 0, (int)nlev, it, it == 1 ? 1 : 0};
+                      RY.data(), MX.data(), MY.data(), ksplt, n, npz, nt, 0, (int)nlev, it, it == 1 ? 1 : 0, exact};
     for (int levc = 0; levc < (int)nlev; ++levc)
       for (int e = 0; e < (int)plane; ++e) prep5_cell<T>(pp, levc, e);
     // edge-halo fill of every plane (complete_group_halo_update, fv_tracer2d.F90:499)
@@ -165,6 +180,7 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
     p.MFX = MX.data();
     p.MFY = MY.data();
     p.AREA = AREA.data();
+    p.RAREA = RAREA.data();
     p.dxa = dxa;
     p.dya = dya;
     p.ksplt = ksplt;
@@ -178,7 +194,7 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
     p.iq0 = 0;
     p.nql = nq;
     p.lim_fac = lim_fac;
-    if (dispatch<T>(p, hord)) return 1;
+    if (exact ? dispatch<T, true>(p, hord) : dispatch<T, false>(p, hord)) return 1;
     for (int t = 0; t < nt; ++t)
       for (int iq = 0; iq < nq; ++iq)
         for (int kz = 0; kz < npz; ++kz) {
@@ -210,9 +226,9 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
   extern "C" int hostsim5_tracer_2d_##S(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area,     \
                                         const T* rarea, const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, \
                                         const int64_t* halo_dst, const int64_t* halo_src, int64_t halo_len, int hord,          \
-                                        T lim_fac, int nsplt, const int* ksplt) {                                              \
+                                        T lim_fac, int nsplt, const int* ksplt, int exact) {                                   \
     return tracer_2d_sim<T>(n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst, halo_src,  \
-                            halo_len, hord, lim_fac, nsplt, ksplt);                                                            \
+                            halo_len, hord, lim_fac, nsplt, ksplt, exact);                                                            \
   }
 API(double, f64)
 API(float, f32)

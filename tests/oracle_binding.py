@@ -72,13 +72,17 @@ def ppm_line(q1, c, dxa, iord, is_, ie, isd, npx, edges, lim_fac=1.0):
     return flux
 
 
-def tracer_2d(case, hord=8, q_split=0, lim_fac=1.0, grid_arrays=None):
+def tracer_2d(case, hord=8, q_split=0, lim_fac=1.0, grid_arrays=None, inplace=False, halo=None):
     """Run the oracle's tracer_2d on (copies of) a synthetic Case.  Returns dict with the post-state of
-    q, dp1, mfx, mfy, cx, cy and nsplt, ksplt, cmax."""
+    q, dp1, mfx, mfy, cx, cy and nsplt, ksplt, cmax.  inplace=True works on the Case's own arrays and `halo` takes a
+    precomputed halo_offsets(n) pair, so that a timed call contains nothing but the oracle itself (bench.py)."""
     s, ct = _sfx(case.dtype)
     g = grid_arrays or case.metrics()
-    out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
-    dst, src = halo_offsets(case.n)
+    if inplace:
+        out = {k: getattr(case, k) for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    else:
+        out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    dst, src = halo if halo is not None else halo_offsets(case.n)
     nsplt = C.c_int(0)
     ksplt = np.zeros(case.npz, dtype=np.int32)
     cmax = np.zeros(case.npz, dtype=case.dtype)
@@ -112,13 +116,14 @@ def tracer_2d_1l(case, hord=8, lim_fac=1.0):
     return out
 
 
-def remap_tracers(q, pe, ak, bk, ptop, kord_tr, fill=True):
-    """q [6, nq, km, n+6, n+6], pe [6, n+2, km+1, n+2] -> (q_out, delp_out [6, km, n+6, n+6])"""
+def remap_tracers(q, pe, ak, bk, ptop, kord_tr, fill=True, inplace=False, delp=None):
+    """q [6, nq, km, n+6, n+6], pe [6, n+2, km+1, n+2] -> (q_out, delp_out [6, km, n+6, n+6]); inplace=True remaps q itself"""
     s, ct = _sfx(q.dtype)
     ntiles, nq, km, nd, _ = q.shape
     n = nd - 6
-    qo = np.array(q, copy=True, order="C")
-    delp = np.zeros((ntiles, km, nd, nd), dtype=q.dtype)
+    qo = q if inplace else np.array(q, copy=True, order="C")
+    if delp is None:
+        delp = np.zeros((ntiles, km, nd, nd), dtype=q.dtype)
     kord = np.ascontiguousarray(np.broadcast_to(np.asarray(kord_tr, dtype=np.int32), (nq,)))
     pe = np.ascontiguousarray(pe, dtype=q.dtype)
     ak = np.ascontiguousarray(ak, dtype=q.dtype)

@@ -27,12 +27,12 @@ def sim5():
     deps = [src] + [os.path.join(csrc, f) for f in ("fv3t_advect5.cuh", "fv3t_advect4.cuh", "fv3t_advect3.cuh", "fv3t_advect2.cuh", "fv3t_advect.cuh",
                                                      "fv3t_ppm.cuh", "fv3t_common.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["nvcc", "-x", "cu", "-O2", "-std=c++17", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
+        subprocess.run(["nvcc", "-x", "cu", "-O1", "-std=c++17", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC,-fno-fast-math", "-shared", "-o", so, src], check=True, cwd=SIM)
     return C.CDLL(so)
 
 
-def run_sim(sim, case, hord, ref, lim_fac=1.0):
+def run_sim(sim, case, hord, ref, lim_fac=1.0, exact=False):
     sfx, ct = ("f64", C.c_double) if case.dtype == np.float64 else ("f32", C.c_float)
     g = case.metrics()
     out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
@@ -42,7 +42,7 @@ def run_sim(sim, case, hord, ref, lim_fac=1.0):
     rc = getattr(sim, f"hostsim5_tracer_2d_{sfx}")(
         case.n, case.npz, case.nq, p(out["q"]), p(out["dp1"]), p(out["mfx"]), p(out["mfy"]), p(out["cx"]), p(out["cy"]),
         p(g["area"]), p(g["rarea"]), p(g["dx"]), p(g["dy"]), p(g["dxa"]), p(g["dya"]), p(g["sin_sg"]), p(dst), p(src),
-        C.c_int64(dst.size), int(hord), ct(lim_fac), int(ref["nsplt"]), p(ksplt))
+        C.c_int64(dst.size), int(hord), ct(lim_fac), int(ref["nsplt"]), p(ksplt), int(bool(exact)))
     assert rc == 0
     return out
 
@@ -55,19 +55,32 @@ def norm_diff(a, b):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("hord", [8, 10, 9, 13, 12, 11, 2])
+@pytest.mark.parametrize("hord", [8, 11, 2])
 def test_advect5_matches_oracle(sim5, oracle, case_factory, hord, dtype):
+    """The schemes with a fast instantiation (fv3t::fast_hord_ok): shared reciprocals, within the north-star bar."""
     case = case_factory(12, 8, 9, dtype)
     ref = oracle.tracer_2d(case, hord=hord)
     got = run_sim(sim5, case, hord, ref)
     nd = norm_diff(got["q"], ref["q"])
-    tol = TOL[case.dtype]
-    if hord == 10:  # discontinuous limiter: the slotted cylinder (tracer 2) flips decisions on rounding noise
-        nd = np.delete(nd, 2)
-    assert nd.max() <= tol, f"hord={hord}: {nd}"
+    assert nd.max() <= TOL[case.dtype], f"hord={hord}: {nd}"
 
 
-@pytest.mark.parametrize("hord", [8, 9])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("hord", [8, 10, 9, 13, 12, 7, 11, -5, 5, 6, 1, 2, 3, 4])
+def test_advect5_exact_instantiation_is_bit_identical(sim5, oracle, case_factory, hord, dtype):
+    """Every scheme in the reference's own operation order (EX = true): bit-identical to the FMA-free oracle, including the
+    caller-visible post-state, with sub-stepping (levels dropping out, lazily advanced dp1)."""
+    case = case_factory(12, 8, 9, dtype, courant=1.8)
+    ref = oracle.tracer_2d(case, hord=hord)
+    got = run_sim(sim5, case, hord, ref, exact=True)
+    sl = slice(NG, -NG)
+    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl]), f"hord={hord}: {norm_diff(got['q'], ref['q'])}"
+    assert np.array_equal(got["dp1"][..., sl, sl], ref["dp1"][..., sl, sl])
+    for k in ("cx", "cy", "mfx", "mfy"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("hord", [8, 11])
 def test_advect5_substeps_and_post_state(sim5, oracle, case_factory, hord):
     """nsplt > 1: the lazily advanced dp1, the 1/ksplt scaling applied at the end, levels dropping out of the sub-step loop."""
     case = case_factory(12, 8, 9, "float64", courant=1.8)
@@ -81,9 +94,14 @@ def test_advect5_substeps_and_post_state(sim5, oracle, case_factory, hord):
         assert np.array_equal(got[k], ref[k]), k
 
 
-def test_advect5_interior_strips_and_blocks(sim5, oracle, case_factory):
-    """C128: three strips (the middle one runs the edge-free x code), 30 interior row blocks."""
-    case = case_factory(128, 2, 3, "float64")
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_advect5_interior_strips_and_blocks(sim5, oracle, case_factory, dtype):
+    """C128: three strips (the middle one runs the edge-free x code), 30 interior row blocks.  fp32: the scalar TMA boxes of
+    strips 1 and 2 start at a column that is not a multiple of four and are read at a shift (A5Stage::shift)."""
+    case = case_factory(128, 2, 3, dtype)
     ref = oracle.tracer_2d(case, hord=8)
     got = run_sim(sim5, case, 8, ref)
-    assert norm_diff(got["q"], ref["q"]).max() <= 1e-12
+    assert norm_diff(got["q"], ref["q"]).max() <= TOL[case.dtype]
+    got = run_sim(sim5, case, 8, ref, exact=True)
+    sl = slice(NG, -NG)
+    assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl])
