@@ -93,11 +93,12 @@ __global__ void k_prep(T* __restrict__ cx, T* __restrict__ cy, T* __restrict__ m
 // (fv_tracer2d.F90:510-515, 547-553); launched only when it /= nsplt.
 template <class T>
 __global__ void k_dp1_update(T* __restrict__ dp1, const T* __restrict__ mfx, const T* __restrict__ mfy, const T* __restrict__ rarea,
-                             const int* __restrict__ ksplt, int n, int npz, int it) {
+                             const int* __restrict__ ksplt, int n, int npz, int it, int mode_1l = 0) {
   const long nd = n + 6, plane = nd * nd;
   const int lev = blockIdx.y;
   const int t = lev / npz, kz = lev % npz;
   if (it > ksplt[kz]) return;
+  if (mode_1l && it >= ksplt[kz]) return;  // tracer_2d_1L: dp1 <- dp2 only between the level's OWN sub-steps (fv_tracer2d.F90:305)
   T* dp = dp1 + (long)lev * plane;
   const T* mx = mfx + (long)lev * (n + 1) * n;
   const T* my = mfy + (long)lev * (n + 1) * n;

@@ -211,6 +211,7 @@ template <class T> struct Cab3Params {
   Pair<T>* cab;
   const int* ksplt;
   int n, npz, it;
+  int mode_1l = 0;  // tracer_2d_1L: dp1 <- dp2 only between the level's own sub-steps (fv_tracer2d.F90:305)
 };
 template <class T> FV3T_HD void cab3_cell(const Cab3Params<T>& p, int t, int kz, int e) {
   const int n = p.n, nd = n + 6;
@@ -218,6 +219,7 @@ template <class T> FV3T_HD void cab3_cell(const Cab3Params<T>& p, int t, int kz,
   const int j = e / n + 1, i = e % n + 1;
   const int ks = p.ksplt[kz];
   if (p.it - 1 > ks) return;
+  if (p.mode_1l && p.it > ks) return;
   const long lev = (long)t * p.npz + kz;
   const long oc = (long)(j + 2) * nd + (i + 2);
   const long ox = (long)(j - 1) * (n + 1) + (i - 1), oy = (long)(j - 1) * n + (i - 1);

@@ -95,6 +95,7 @@ template <class T> struct Prep5Params {
   const int* ksplt;
   int n, npz, ntiles, lev0, nlev, it, mode_all;
   int exact;  // 1: scratch for the exact-arithmetic instantiations (ra_x, ra_y, {dp1, dp2}); 0: reciprocals and {dp1/dp2, rarea/2dp2}
+  int mode_1l = 0;  // tracer_2d_1L: dp1 <- dp2 only between the level's own sub-steps (fv_tracer2d.F90:305)
 };
 
 template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, int e) {
@@ -104,6 +105,7 @@ template <class T> FV3T_HD void prep5_cell(const Prep5Params<T>& p, int levc, in
   const int t = (int)(lev / p.npz), kz = (int)(lev % p.npz);
   const int ks = p.ksplt[kz];
   if (p.it - 1 > ks) return;  // the level took no part in sub-step it-1: nothing changes any more
+  if (p.mode_1l && p.it > ks) return;
   const int j = e / nd - 2, i = e % nd - 2;
   const T frac = T(1) / (T)ks;
   const T* area = p.g.area + (long)t * plane;

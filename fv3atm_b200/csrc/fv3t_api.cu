@@ -138,6 +138,7 @@ template <class T> struct Impl {
   bool maps5_ok = false;
   bool use5 = true;            // FV3T_ADV5=0 keeps the per-tracer k_advect4
   bool call5 = false;          // the current tracer_2d call runs k_advect5
+  bool mode_1l = false;        // the current call is tracer_2d_1L: the dp1 post-state of fv_tracer2d.F90:305
   bool exact5 = false;         // ... its exact-arithmetic instantiation (schemes outside fast_hord_ok: bit-identical to the oracle)
   bool scale_pending = false;  // k_advect5 path: the in-place 1/ksplt scaling of cx, cy, mfx, mfy is applied by finish()
   fv3t::Pair<T>* P1 = nullptr;  // fast remap: spline / overlap coefficients per column (fv3t_remap3.cuh)
@@ -237,7 +238,7 @@ template <class T> struct Impl {
   int alloc5();
   int finish();
   int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
-  int remap_resident(int nq, const int* kord, int fill, int j_first, int j_count);
+  int remap_resident(int nq, const int* kord, int fill, int j_first, int j_count, const T* pe2_ext = nullptr, const T* dp2_ext = nullptr);
   int remap_prepare();
   int launch_coef_side();
   int tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const T* hpe, const T* hak, const T* hbk, T hptop, T* hdelp, int nq,
@@ -626,7 +627,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     if (!fv3t::adv5_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
     if (it > 1) {  // dp1 <- dp2 of sub-step it-1 (fv_tracer2d.F90:547-553), then dp1/dp2, 0.5*rarea/dp2 of this sub-step
       fv3t::Prep5Params<T> pp{cx, cy, mfx, mfy, dp1, fv3t::GridDev<T>{area, rarea, dx, dy, dxa, dya, sin_sg}, X5, Y5, C5, RX5, RY5, MX5, MY5,
-                              ksplt_d, n, npz, nt, 0, nt * npz, it, 0, exact5 ? 1 : 0};
+                              ksplt_d, n, npz, nt, 0, nt * npz, it, 0, exact5 ? 1 : 0, mode_1l ? 1 : 0};
       kbegin();
       CK(fv3t::fast_prep5<T>(pp, stream));
       kend(KC_SCALE);
@@ -670,7 +671,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   if (call_fast) {
     if (!fv3t::fast_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
     if (it > 1) {  // dp1 <- dp2 of sub-step it-1 (fv_tracer2d.F90:547-553), then dp1/dp2, 0.5*rarea/dp2 of this sub-step
-      fv3t::Cab3Params<T> cp{dp1, mfx, mfy, rarea, cab, ksplt_d, n, npz, it};
+      fv3t::Cab3Params<T> cp{dp1, mfx, mfy, rarea, cab, ksplt_d, n, npz, it, mode_1l ? 1 : 0};
       kbegin();
       CK(fv3t::fast_cab3<T>(cp, nt, stream));
       kend(KC_SCALE);
@@ -751,7 +752,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
   if (it != nsplt) {
     dim3 grid(8, nt * npz);
     kbegin();
-    fv3t::k_dp1_update<T><<<grid, 256, 0, stream>>>(dp1, mfx, mfy, rarea, ksplt_d, n, npz, it);
+    fv3t::k_dp1_update<T><<<grid, 256, 0, stream>>>(dp1, mfx, mfy, rarea, ksplt_d, n, npz, it, mode_1l ? 1 : 0);
     kend(KC_SCALE);
     CK(cudaGetLastError());
   }
@@ -829,18 +830,20 @@ template <class T, int G, bool MAPN> int launch_remap2(Impl<T>& c, const fv3t::R
 
 // Tracer part of Lagrangian_to_Eulerian for rows js+j_first .. (fv_mapz.F90:261-273, 343-368, 407-426): reads q[cur],
 // writes q[cur^1]; a whole-tile call (j_count == n) makes the written buffer the current one.
-template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill, int j_first, int j_count) {
+template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill, int j_first, int j_count, const T* pe2_ext, const T* dp2_ext) {
   if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
-  if (!have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
+  if (!have_vertical && !pe2_ext) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
   CK(cudaSetDevice(device));
   CK(cudaMemcpyAsync(kord_d, kord, nq * sizeof(int), cudaMemcpyHostToDevice, stream));
-  const bool mapn = nq > 5;  // fv_mapz.F90:410: mapn_tracer for nq > 5, else map1_q2 + fillz per tracer
+  // fv_mapz.F90:410: mapn_tracer for nq > 5, else map1_q2 + fillz per tracer; the row-granular mapn_tracer entry (pe2_ext set)
+  // IS mapn_tracer whatever nq
+  const bool mapn = nq > 5 || pe2_ext != nullptr;
   bool need_ppm = false;     // map1_q2 sends kord <= 7 to ppm_profile (fv_mapz.F90:1544-1548)
   if (!mapn)
     for (int iq = 0; iq < nq; ++iq) need_ppm |= kord[iq] <= 7;
   int rc = 0;
   if (coef_ready) CK(cudaStreamWaitEvent(stream, ev_coef, 0));  // remap_prepare's side-stream kernel also writes delp
-  bool fast_ok = fast && mapn && j_count == n && npz <= 128;
+  bool fast_ok = fast && mapn && j_count == n && npz <= 128 && !pe2_ext;
   const int ak0 = kord[0] < 0 ? -kord[0] : kord[0];
   for (int iq = 0; iq < nq; ++iq) {
     const int a = kord[iq] < 0 ? -kord[iq] : kord[iq];
@@ -915,6 +918,8 @@ template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill
     p.fill = fill;
     p.j_first = j_first;
     p.j_count = j_count;
+    p.pe2_ext = pe2_ext;
+    p.dp2_ext = dp2_ext;
     static const int gsel = getenv("FV3T_REMAP_G") ? atoi(getenv("FV3T_REMAP_G")) : 1;  // tuning knob (tracers per thread)
     if (gsel == 1)
       rc = mapn ? launch_remap2<T, 1, true>(*this, p) : launch_remap2<T, 1, false>(*this, p);
@@ -1232,6 +1237,16 @@ extern "C" int fv3t_device_count(void) {
     }                                                                                                                          \
     return 0;                                                                                                                  \
   }                                                                                                                            \
+  extern "C" int fv3t_##P##_tracer_2d_1L(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,  \
+                                         int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out,         \
+                                         int* ksplt_out) {                                                                     \
+    NEED(ctx, P);                                                                                                              \
+    (void)q_split; /* not used by tracer_2d_1L (fv_tracer2d.F90:92-321) */                                                     \
+    I->mode_1l = true;                                                                                                         \
+    const int rc = fv3t_##P##_tracer_2d(ctx, q, dp1, mfx, mfy, cx, cy, nq, hord, 0, nord_tr, trdm, lim_fac, nsplt_out, ksplt_out); \
+    I->mode_1l = false;                                                                                                        \
+    return rc;                                                                                                                 \
+  }                                                                                                                            \
   extern "C" int fv3t_##P##_remap_tracers(fv3t_ctx* ctx, const REAL* pe, const REAL* ak, const REAL* bk, REAL ptop, REAL* q,   \
                                           REAL* delp, int nq, const int* kord_tr, int fill) {                                  \
     NEED(ctx, P);                                                                                                              \
@@ -1248,13 +1263,12 @@ extern "C" int fv3t_device_count(void) {
                                         const REAL* dp2, const int* kord, int j, int i1, int i2, int isd, int ied, int jsd,   \
                                         int jed, REAL q_min, int fill) {                                                       \
     NEED(ctx, P);                                                                                                              \
-    (void)pe2;                                                                                                                 \
-    (void)dp2;                                                                                                                 \
+    if (!pe1 || !pe2 || !q1 || !dp2 || !kord) return fail("fv3tracer: null argument");                                         \
     if (km != I->npz || i1 != 1 || i2 != I->n || isd != -2 || ied != I->n + 3 || jsd != -2 || jed != I->n + 3)                 \
       return fail("fv3tracer: mapn_tracer bounds do not match the context (whole-tile rows only)");                           \
     if (q_min != REAL(0)) return fail("fv3tracer: mapn_tracer is only called with q_min = 0 on this path");                   \
     if (I->nt != 1) return fail("fv3tracer: the row-granular mapn_tracer entry needs a one-tile context");                    \
-    if (!I->have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");                          \
+    if (nq < 1 || nq > I->nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, I->nqmax);                       \
     std::lock_guard<std::mutex> lk(I->row_mutex);                                                                              \
     CK(cudaSetDevice(I->device));                                                                                              \
     const size_t nd = I->n + 6, pl = nd * nd;                                                                                  \
@@ -1264,7 +1278,12 @@ extern "C" int fv3t_device_count(void) {
     /* q rows: (isd:ied) of row j for every (k, iq) */                                                                         \
     CK(cudaMemcpy2DAsync(I->q[I->cur] + (size_t)(j + 2) * nd, pl * sizeof(REAL), q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), \
                          nd * sizeof(REAL), (size_t)km * nq, cudaMemcpyHostToDevice, I->stream));                              \
-    int rc = I->remap_resident(nq, kord, fill, j - 1, 1);                                                                      \
+    /* the caller's target grid: pe2 (i1:i2, km+1) and dp2 (i1:i2, km) of this row, consumed as given */                      \
+    const size_t npe2 = (size_t)I->n * (km + 1), ndp2 = (size_t)I->n * km;                                                     \
+    if (!I->row_buf) CK(cudaMalloc((void**)&I->row_buf, (npe2 + ndp2) * sizeof(REAL)));                                        \
+    CK(cudaMemcpyAsync(I->row_buf, pe2, npe2 * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                              \
+    CK(cudaMemcpyAsync(I->row_buf + npe2, dp2, ndp2 * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                       \
+    int rc = I->remap_resident(nq, kord, fill, j - 1, 1, I->row_buf, I->row_buf + npe2);                                       \
     if (rc) return rc;                                                                                                         \
     CK(cudaMemcpy2DAsync(q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), I->q[I->cur ^ 1] + (size_t)(j + 2) * nd,                \
                          pl * sizeof(REAL),                                                                                    \

@@ -28,6 +28,10 @@ template <class T> struct Remap2Params {
   T ptop;
   int n, km, nq, ntiles, fill;
   int j_first, j_count;
+  // Row-granular mapn_tracer entry (fv_mapz.F90:1386-1402): the CALLER's target grid of row j_first, pe2 (i1:i2, km+1) and
+  // dp2 (i1:i2, km) on the device; null = pe2 = ak + bk*pe1(km+1) as Lagrangian_to_Eulerian builds it (fv_mapz.F90:263-272)
+  const T* pe2_ext = nullptr;
+  const T* dp2_ext = nullptr;
 };
 
 // limited parabola of an interior layer 3 <= k <= km-2 (fv_mapz.F90:1886-2073), iv = 0, qmin = 0.
@@ -162,7 +166,12 @@ FV3T_HD void remap_column(const Remap2Params<T>& p, int t, int i, int j, int iq0
     if (k <= km + 1) prefetch_l1(pe + (long)(k - 1) * pe_ld1);
   };
   const T ps = PE1(km + 1);
-  auto PE2 = [&](int k) -> T { return k == 1 ? p.ptop : (k == km + 1 ? ps : p.ak[k - 1] + p.bk[k - 1] * ps); };
+  auto PE2 = [&](int k) -> T {
+    if (p.pe2_ext) return p.pe2_ext[(long)(k - 1) * n + (i - 1)];
+    return k == 1 ? p.ptop : (k == km + 1 ? ps : p.ak[k - 1] + p.bk[k - 1] * ps);
+  };
+  // dp2(k) given its two interfaces: the caller's own array when the target grid is the caller's
+  auto DP2 = [&](int k, T lo, T hi) -> T { return p.dp2_ext ? p.dp2_ext[(long)(k - 1) * n + (i - 1)] : hi - lo; };
 
   T gam[KM + 2];
   T qv[G][KM + 2];
@@ -307,10 +316,10 @@ FV3T_HD void remap_column(const Remap2Params<T>& p, int t, int i, int j, int iq0
   // target-layer state (shared by the tracers): pe2(k), pe2(k+1), dp2(k-2..k)
   int k = 1;
   T pe2k = PE2(1), pe2k1 = PE2(2);
-  T dpk = pe2k1 - pe2k, dpk_m1 = T(0), dpk_m2 = T(0);
+  T dpk = DP2(1, pe2k, pe2k1), dpk_m1 = T(0), dpk_m2 = T(0);
   bool started = false;
   T* delp = p.delp + (long)t * plane * km + col;
-  const bool wdelp = iq0 == 0;
+  const bool wdelp = iq0 == 0 && !p.pe2_ext;  // mapn_tracer itself never writes delp
   if (wdelp) delp[0] = dpk;
 
   auto finalize = [&](int g, int kk, T x, T dpkk) {
@@ -377,7 +386,7 @@ FV3T_HD void remap_column(const Remap2Params<T>& p, int t, int i, int j, int iq0
       pe2k1 = PE2(k + 1);
       dpk_m2 = dpk_m1;
       dpk_m1 = dpk;
-      dpk = pe2k1 - pe2k;
+      dpk = DP2(k, pe2k, pe2k1);
       if (wdelp) delp[(long)(k - 1) * plane] = dpk;
     }
   };
@@ -514,7 +523,7 @@ FV3T_HD void remap_column(const Remap2Params<T>& p, int t, int i, int j, int iq0
       if (zfix[g] && sum0[g] > T(0) && live[g]) {
         const T fac = sum0[g] / sum1[g];
         for (int kk = 2; kk <= km; ++kk) {
-          const T dp = PE2(kk + 1) - PE2(kk);
+          const T dp = DP2(kk, PE2(kk), PE2(kk + 1));
           const T x = qd[g][(long)(kk - 1) * plane];
           qd[g][(long)(kk - 1) * plane] = f_max(T(0), fac * (x * dp) / dp);
         }

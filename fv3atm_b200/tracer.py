@@ -66,6 +66,18 @@ class TracerContext:
                                      C.byref(nsplt), L.ptr(ksplt)))
         return nsplt.value, ksplt
 
+    def tracer_2d_1L(self, q, dp1, mfx, mfy, cx, cy, hord, nord_tr=0, trdm=0.0, lim_fac=1.0):
+        """tracer_2d_1L (fv_tracer2d.F90:92-321, the z_tracer variant): same q / cx / cy / mfx / mfy post-state as tracer_2d, dp1
+        advanced only between a level's own sub-steps.  Returns (max over k of the per-level sub-step count, the counts)."""
+        nq = q.shape[1]
+        for a in (q, dp1, mfx, mfy, cx, cy):
+            assert a.dtype == self.dtype and a.flags["C_CONTIGUOUS"]
+        nsplt = C.c_int(0)
+        ksplt = np.zeros(self.npz, dtype=np.int32)
+        L.check(self._f("tracer_2d_1L")(self._h, L.ptr(q), L.ptr(dp1), L.ptr(mfx), L.ptr(mfy), L.ptr(cx), L.ptr(cy), int(nq),
+                                        int(hord), 0, int(nord_tr), self._ct(trdm), self._ct(lim_fac), C.byref(nsplt), L.ptr(ksplt)))
+        return nsplt.value, ksplt
+
     def remap_tracers(self, pe, ak, bk, ptop, q, delp, kord_tr, fill=True):
         """Tracer part of Lagrangian_to_Eulerian for every row: q and delp updated in place."""
         nq = q.shape[1]

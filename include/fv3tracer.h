@@ -48,7 +48,7 @@ typedef struct fv3t_dims {
 
 /* Device-resident fields addressable through fv3t_*_upload/download/device_ptr */
 enum fv3t_field {
-  FV3T_Q = 0,   /* tracers; after tracer_2d a level may live in either ping-pong buffer: download gathers    */
+  FV3T_Q = 0,   /* tracers (two ping-pong buffers; outside a tracer_2d call every level lives in the current one) */
   FV3T_DP1 = 1, /* delp before dyn_core (updated in place between sub-steps, fv_tracer2d.F90:547-553)        */
   FV3T_MFX = 2,
   FV3T_MFY = 3,
@@ -84,6 +84,14 @@ int fv3t_device_count(void);
   int fv3t_##P##_tracer_2d(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,         \
                            int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out, int* ksplt_out); \
                                                                                                                         \
+  /* tracer_2d_1L(q, dp1, mfx, mfy, cx, cy, gridstruct, bd, domain, npx, npy, npz, nq, hord, q_split, dt, id_divg, q_pack,        \
+                  dp1_pack, nord_tr, trdm, lim_fac)                  ACS/model/fv_tracer2d.F90:92-113, called for z_tracer        \
+     (fv_dynamics.F90:696-698).  Same arguments and the same q, cx, cy, mfx, mfy post-state as tracer_2d (the per-level         \
+     sub-step counts of :201-202 are the ksplt(k) of tracer_2d); the dp1 post-state differs: a level's dp1 is advanced          \
+     between ITS OWN sub-steps only (:305), i.e. ksplt(k)-1 times.  q_split is not used by the routine. */                      \
+  int fv3t_##P##_tracer_2d_1L(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,         \
+                              int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out, int* ksplt_out); \
+                                                                                                                        \
   /* Tracer part of Lagrangian_to_Eulerian for all rows js..je at once (the j loop of fv_mapz.F90:261 hoisted):        \
      pe1 = pe(:,:,j); pe2 = ak + bk*pe(:,km+1,j); dp2; delp <- dp2 (:263-272,350-368); then mapn_tracer (nq > 5) or   \
      map1_q2 + fillz per tracer (:410-426).  q and delp are updated in place on the compute domain. */                 \
@@ -92,8 +100,10 @@ int fv3t_device_count(void);
                                                                                                                         \
   /* mapn_tracer(nq, km, pe1, pe2, q1, dp2, kord, j, i1, i2, isd, ied, jsd, jed, q_min, fill)   fv_mapz.F90:1386-1402  \
      Row-granular compatibility entry with the reference's own argument list (one tile, one row j; pe1, pe2           \
-     (i1:i2, km+1), dp2 (i1:i2, km), q1 (isd:ied, jsd:jed, km, nq)).  Thread-safe (the reference calls it from an      \
-     OpenMP loop over j, fv_mapz.F90:250-261); serialised internally.  Prefer fv3t_*_remap_tracers. */                 \
+     (i1:i2, km+1), dp2 (i1:i2, km), q1 (isd:ied, jsd:jed, km, nq)).  pe2 and dp2 are consumed AS GIVEN (any target      \
+     grid, not only ak + bk*ps) and the profile is always scalar_profile, whatever nq -- it is mapn_tracer, not the    \
+     nq-dependent dispatch of Lagrangian_to_Eulerian.  Thread-safe (the reference calls it from an OpenMP loop over j,  \
+     fv_mapz.F90:250-261); serialised internally.  Prefer fv3t_*_remap_tracers. */                 \
   int fv3t_##P##_mapn_tracer(fv3t_ctx* ctx, int nq, int km, const REAL* pe1, const REAL* pe2, REAL* q1, const REAL* dp2, \
                              const int* kord, int j, int i1, int i2, int isd, int ied, int jsd, int jed, REAL q_min,   \
                              int fill);                                                                                 \
@@ -141,7 +151,9 @@ FV3T_DECLARE(f32, float)
 /* Precision-independent calls */
 int fv3t_destroy(fv3t_ctx* ctx);
 int fv3t_sync(fv3t_ctx* ctx);
-void* fv3t_device_ptr(fv3t_ctx* ctx, int field); /* base of the device mirror (FV3T_Q: buffer 0)             */
+/* Base of the device mirror.  FV3T_Q: the buffer that CURRENTLY holds the tracers -- tracer_2d (odd nsplt) and the remap
+   write the other ping-pong buffer and flip it, so the pointer is valid only until the next tracer_2d / remap call.   */
+void* fv3t_device_ptr(fv3t_ctx* ctx, int field);
 size_t fv3t_halo_strip_elems(fv3t_ctx* ctx);     /* elements of one packed edge strip: 3*(npx-1)*npz*nq_cur  */
 int fv3t_neighbor(fv3t_ctx* ctx, int global_tile, int edge, int* nbr_tile, int* nbr_edge, int* rotated);
 uint64_t fv3t_kernel_launches(fv3t_ctx* ctx);    /* kernels launched by this context so far (bench accounting) */

@@ -375,3 +375,60 @@ def test_tracer_step_equals_the_two_separate_calls(oracle, case_factory, courant
     for k in ("cx", "cy", "mfx", "mfy"):
         assert np.array_equal(a[k], b[k]), k
     assert launches > 0
+
+
+# ---- boundary: tracer_2d_1L and the row-granular mapn_tracer with the caller's own target grid ----------------------------------
+@pytest.mark.parametrize("hord", [8, 10])
+def test_tracer_2d_1l_entry(oracle, case_factory, hord, mode):
+    """fv3t_*_tracer_2d_1L (fv_tracer2d.F90:92-321, z_tracer): q as tracer_2d; cx, cy, mfx, mfy and -- unlike tracer_2d -- the dp1
+    post-state of a level advanced only between its own sub-steps (:305), all bit-identical to the oracle's tracer_2d_1L."""
+    case = case_factory(24, 16, 9, "float64", courant=3.3)
+    ref = oracle.tracer_2d_1l(case, hord=hord)
+    std = oracle.tracer_2d(case, hord=hord)
+    assert len(set(ref["ksplt"].tolist())) > 1 and not np.array_equal(ref["dp1"], std["dp1"])   # the two routines do differ here
+    ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+    out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    nsplt, ksplt = ctx.tracer_2d_1L(out["q"], out["dp1"], out["mfx"], out["mfy"], out["cx"], out["cy"], hord)
+    ctx.close()
+    assert nsplt == ref["nsplt"] and np.array_equal(ksplt, ref["ksplt"])
+    check_q(out["q"], ref["q"], mode, "float64", bit_exact_expected=hord not in FAST_HORD, what=f"1L hord={hord}")
+    sl = slice(NG, -NG)
+    assert np.array_equal(out["dp1"][..., sl, sl], ref["dp1"][..., sl, sl])
+    for k in ("cx", "cy", "mfx", "mfy"):
+        assert np.array_equal(out[k], ref[k]), k
+
+
+@pytest.mark.parametrize("nq", [3, 9])
+def test_mapn_tracer_consumes_the_callers_target_grid(oracle, case_factory, nq, mode):
+    """fv3t_*_mapn_tracer with a pe2 / dp2 that is NOT ak + bk*ps, and with nq <= 5 (where Lagrangian_to_Eulerian itself would
+    have dispatched to map1_q2): the entry is mapn_tracer -- scalar_profile always, the caller's target grid as given -- and
+    must equal the oracle's mapn_tracer column by column, bit for bit (strict kernel)."""
+    import oracle_binding as ob
+    case = case_factory(12, 16, 9, "float64")
+    n, km = case.n, case.npz
+    g = {k: v[:1] for k, v in case.metrics().items()}
+    ctx = TracerContext(n + 1, km, nq, g, dtype=case.dtype, tiles=(1,))
+    q1 = np.ascontiguousarray(case.q[0, :nq])
+    q_in = q1.copy()
+    kord = np.full(nq, 9, dtype=np.int32)
+    rng = np.random.default_rng(7)
+    rows = (1, 5, n)
+    pe2_rows = {}
+    for j in rows:
+        pe1 = np.ascontiguousarray(case.pe[0, j, :, 1:-1])    # (km+1, n)
+        w = rng.uniform(-0.3, 0.3, size=pe1.shape)
+        pe2 = pe1 + w * np.gradient(pe1, axis=0)               # an arbitrary monotone target grid with the same ends
+        pe2[0], pe2[-1] = pe1[0], pe1[-1]
+        pe2 = np.ascontiguousarray(np.sort(pe2, axis=0))
+        dp2 = np.ascontiguousarray(np.diff(pe2, axis=0))
+        pe2_rows[j] = (pe1, pe2)
+        ctx.mapn_tracer(nq, km, pe1, pe2, q1, dp2, kord, j, 1, n, -2, n + 3, -2, n + 3, 0.0, True)
+    ctx.close()
+    for j in rows:
+        pe1, pe2 = pe2_rows[j]
+        for i in range(n):
+            col = np.ascontiguousarray(q_in[:, :, j + 2, i + 3])      # [nq, km]
+            want = ob.map_col(0, pe1[:, i], pe2[:, i], col, kord, q_min=0.0, fill=True)
+            assert np.array_equal(q1[:, :, j + 2, i + 3], want), (j, i)
+    untouched = [j for j in range(1, n + 1) if j not in rows]
+    assert np.array_equal(q1[:, :, [j + 2 for j in untouched]], q_in[:, :, [j + 2 for j in untouched]])
