@@ -170,6 +170,10 @@ template <class T> struct Impl {
   uint64_t launches = 0;
   std::mutex row_mutex;
   T* row_buf = nullptr;  // staging for the row-granular mapn_tracer entry
+  T* fld = nullptr;        // device staging of one scalar field (map_scalar / map1_ppm entries), sized like delp
+  T* fld_qs = nullptr;     // its bottom boundary values (iv = -2)
+  T* strip_buf = nullptr;  // device staging of one packed edge strip (halo_pack_host / halo_unpack_host)
+  size_t strip_cap = 0;
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool prof = false;
@@ -364,7 +368,7 @@ template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
   void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, RAREA5, coef4, neg4, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
-                  ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf};
+                  ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf, strip_buf, fld, fld_qs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int s = 0; s < 6; ++s)
@@ -1259,6 +1263,40 @@ extern "C" int fv3t_device_count(void) {
     if ((rc = I->download(FV3T_Q, q, nq))) return rc;                                                                          \
     return I->download(FV3T_DELP, delp, nq);                                                                                   \
   }                                                                                                                            \
+  extern "C" int fv3t_##P##_map_field(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord, REAL q_min, int use_cs) {        \
+    NEED(ctx, P);                                                                                                              \
+    if (!q) return fail("fv3tracer: null argument");                                                                           \
+    if (!I->have_vertical) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");                          \
+    if (iv == -2 && !qs) return fail("fv3tracer: iv = -2 needs the bottom boundary values qs");                               \
+    if (iv < -2 || iv > 2) return fail("fv3tracer: iv = %d is not a mode of scalar_profile / cs_profile", iv);                \
+    CK(cudaSetDevice(I->device));                                                                                              \
+    const size_t ne = I->sz_c() * I->nt, n2 = I->plane() * I->nt;                                                              \
+    if (!I->fld) CK(cudaMalloc((void**)&I->fld, ne * sizeof(REAL)));                                                           \
+    CK(cudaMemcpyAsync(I->fld, q, ne * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                                      \
+    if (qs) {                                                                                                                  \
+      if (!I->fld_qs) CK(cudaMalloc((void**)&I->fld_qs, n2 * sizeof(REAL)));                                                   \
+      CK(cudaMemcpyAsync(I->fld_qs, qs, n2 * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                                \
+    }                                                                                                                          \
+    fv3t::MapFieldParams<REAL> p{I->fld, qs ? I->fld_qs : nullptr, I->pe, I->ak, I->bk, I->ptop, q_min, I->n, I->npz, I->nt, iv, kord, \
+                                 use_cs ? 1 : 0};                                                                              \
+    dim3 grid((I->n * I->n + 63) / 64, I->nt);                                                                                 \
+    I->kbegin();                                                                                                               \
+    if (I->npz <= 64)                                                                                                          \
+      fv3t::k_map_field<REAL, 64><<<grid, 64, 0, I->stream>>>(p);                                                              \
+    else                                                                                                                       \
+      fv3t::k_map_field<REAL, 128><<<grid, 64, 0, I->stream>>>(p);                                                             \
+    I->kend(KC_REMAP);                                                                                                         \
+    CK(cudaGetLastError());                                                                                                    \
+    CK(cudaMemcpyAsync(q, I->fld, ne * sizeof(REAL), cudaMemcpyDeviceToHost, I->stream));                                      \
+    CK(cudaStreamSynchronize(I->stream));                                                                                      \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_map_scalar(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord, REAL q_min) {                 \
+    return fv3t_##P##_map_field(ctx, q, qs, iv, kord, q_min, 0);                                                               \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_map1_ppm(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord) {                               \
+    return fv3t_##P##_map_field(ctx, q, qs, iv, kord, REAL(0), 1);                                                             \
+  }                                                                                                                            \
   extern "C" int fv3t_##P##_mapn_tracer(fv3t_ctx* ctx, int nq, int km, const REAL* pe1, const REAL* pe2, REAL* q1,             \
                                         const REAL* dp2, const int* kord, int j, int i1, int i2, int isd, int ied, int jsd,   \
                                         int jed, REAL q_min, int fill) {                                                       \
@@ -1310,6 +1348,40 @@ extern "C" int fv3t_device_count(void) {
   extern "C" int fv3t_##P##_halo_unpack(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* dev_buf) {                \
     NEED(ctx, P);                                                                                                              \
     return I->halo_pack(it, local_tile, edge, const_cast<REAL*>(dev_buf), true);                                               \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_pack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* host_buf) {                  \
+    NEED(ctx, P);                                                                                                              \
+    const size_t ne = (size_t)3 * I->n * I->npz * I->nq_cur;                                                                   \
+    if (!host_buf || ne == 0) return fail("fv3tracer: halo_pack_host: null buffer or no resident tracers");                   \
+    CK(cudaSetDevice(I->device));                                                                                              \
+    if (I->strip_cap < ne) {                                                                                                   \
+      if (I->strip_buf) cudaFree(I->strip_buf);                                                                                \
+      I->strip_buf = nullptr;                                                                                                  \
+      CK(cudaMalloc((void**)&I->strip_buf, ne * sizeof(REAL)));                                                                \
+      I->strip_cap = ne;                                                                                                       \
+    }                                                                                                                          \
+    const int rc = I->halo_pack(it, local_tile, edge, I->strip_buf, false);                                                    \
+    if (rc) return rc;                                                                                                         \
+    CK(cudaMemcpyAsync(host_buf, I->strip_buf, ne * sizeof(REAL), cudaMemcpyDeviceToHost, I->stream));                         \
+    CK(cudaStreamSynchronize(I->stream));                                                                                      \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_unpack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* host_buf) {          \
+    NEED(ctx, P);                                                                                                              \
+    const size_t ne = (size_t)3 * I->n * I->npz * I->nq_cur;                                                                   \
+    if (!host_buf || ne == 0) return fail("fv3tracer: halo_unpack_host: null buffer or no resident tracers");                 \
+    CK(cudaSetDevice(I->device));                                                                                              \
+    if (I->strip_cap < ne) {                                                                                                   \
+      if (I->strip_buf) cudaFree(I->strip_buf);                                                                                \
+      I->strip_buf = nullptr;                                                                                                  \
+      CK(cudaMalloc((void**)&I->strip_buf, ne * sizeof(REAL)));                                                                \
+      I->strip_cap = ne;                                                                                                       \
+    }                                                                                                                          \
+    CK(cudaMemcpyAsync(I->strip_buf, host_buf, ne * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                         \
+    const int rc = I->halo_pack(it, local_tile, edge, I->strip_buf, true);                                                     \
+    if (rc) return rc;                                                                                                         \
+    CK(cudaStreamSynchronize(I->stream));                                                                                      \
+    return 0;                                                                                                                  \
   }                                                                                                                            \
   extern "C" int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac) {                                 \
     NEED(ctx, P);                                                                                                              \

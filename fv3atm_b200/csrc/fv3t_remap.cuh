@@ -122,8 +122,11 @@ template <class T, int KM> struct ColWork {
   unsigned char fl[KM + 3];  // bit0 extm, bit1 ext5, bit2 ext6
 };
 
-// scalar_profile (fv_mapz.F90:1691-2096) with iv = 0 semantics parameterised; qs is never read for iv /= -2.
-template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w, int km, int iv, int kord, T qmin) {
+// scalar_profile (fv_mapz.F90:1691-2096; SCALAR = true) and cs_profile (:2098-2498; SCALAR = false) for one column.  The two
+// reference routines share the spline, the interface constraints and the limiter cascade; cs_profile has no qmin (the
+// |kord| = 9, 11, 15 branches differ) and forms a6 of |kord| = 9 as 6*a1 - 3*(a2+a3) (:2324) where scalar_profile has
+// 3*(2*a1 - (a2+a3)) (:1921) -- a different rounding.  qs (bottom boundary value) is read for iv = -2 only.
+template <class T, int KM, bool SCALAR> __device__ void profile_col(ColWork<T, KM>& w, int km, int iv, int kord, T qmin, T qs) {
   T* a1 = w.a1;
   T* a2 = w.a2;
   T* a3 = w.a3;
@@ -134,7 +137,20 @@ template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w,
   unsigned char* fl = w.fl;
   const int akord = kord < 0 ? -kord : kord;
   T d4 = T(0);
-  {
+  if (iv == -2) {  // spline with the bottom interface value given (fv_mapz.F90:1719-1735 / :2126-2142)
+    gam[2] = T(0.5);
+    q[1] = T(1.5) * a1[1];
+    for (int k = 2; k <= km - 1; ++k) {
+      const T grat = delp[k - 1] / delp[k];
+      const T bet = T(2) + grat + grat - gam[k];
+      q[k] = (T(3) * (a1[k - 1] + a1[k]) - q[k - 1]) / bet;
+      gam[k + 1] = grat / bet;
+    }
+    const T grat = delp[km - 1] / delp[km];
+    q[km] = (T(3) * (a1[km - 1] + a1[km]) - grat * qs - q[km - 1]) / (T(2) + grat + grat - gam[km]);
+    q[km + 1] = qs;
+    for (int k = km - 1; k >= 1; --k) q[k] = q[k] - gam[k + 1] * q[k + 1];
+  } else {
     const T grat = delp[2] / delp[1];
     T bet = grat * (grat + T(0.5));
     q[1] = ((grat + grat) * (grat + T(1)) * a1[1] + a1[2]) / bet;
@@ -231,14 +247,14 @@ template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w,
       huynh();
       set_a6();
     } else if (akord == 9) {
-      if ((extm && extm_m) || (extm && extm_p) || (extm && a1k < qmin)) {
+      if ((extm && extm_m) || (extm && extm_p) || (SCALAR && extm && a1k < qmin)) {
         flat();
         a4k = T(0);
       } else {
-        set_a6();
+        if (SCALAR) set_a6(); else a4k = T(6) * a1k - T(3) * (a2k + a3k);
         if (f_abs(a4k) > f_abs(a2k - a3k)) {
           huynh();
-          set_a6();
+          if (SCALAR) set_a6(); else a4k = T(6) * a1k - T(3) * (a2k + a3k);
         }
       }
     } else if (akord == 10) {
@@ -268,10 +284,18 @@ template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w,
     } else if (akord == 14) {
       set_a6();
     } else if (akord == 15) {
-      if ((ext5 && ext5_m) || (ext5 && ext5_p) || (ext5 && a1k < qmin))
-        flat();
-      else if (ext6)
-        huynh();
+      if (SCALAR) {
+        if ((ext5 && ext5_m) || (ext5 && ext5_p) || (ext5 && a1k < qmin))
+          flat();
+        else if (ext6)
+          huynh();
+      } else {  // cs_profile (:2394-2404): the ext6 branch is reached only when ext5 is false
+        if (ext5) {
+          if (ext5_m || ext5_p) flat();
+        } else if (ext6) {
+          huynh();
+        }
+      }
       set_a6();
     } else if (akord == 16) {
       if (ext5) {
@@ -282,7 +306,7 @@ template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w,
       }
       set_a6();
     } else {  // 11
-      if (ext5 && (ext5_m || ext5_p || a1k < qmin)) {
+      if (ext5 && (ext5_m || ext5_p || (SCALAR && a1k < qmin))) {
         flat();
         a4k = T(0);
       } else {
@@ -303,6 +327,10 @@ template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w,
     a4[k] = T(3) * (T(2) * a1[k] - (a2[k] + a3[k]));
     cs_limiters1<T>(fl[k] & 1, a1[k], a2[k], a3[k], a4[k], k == km ? 1 : 2);
   }
+}
+
+template <class T, int KM> __device__ void scalar_profile_col(ColWork<T, KM>& w, int km, int iv, int kord, T qmin) {
+  profile_col<T, KM, true>(w, km, iv, kord, qmin, T(0));
 }
 
 // ppm_profile (fv_mapz.F90:2580-2837), reached through map1_q2 when kord <= 7.  Scratch: gam <- dc,
@@ -557,6 +585,53 @@ template <class T, int KM> __global__ void __launch_bounds__(64) k_remap(const R
     if (p.fill) fillz_col<T, KM>(w, km);
     for (int k = 1; k <= km; ++k) p.qout[qoff + (long)(k - 1) * plane] = w.q2[k];
   }
+}
+
+// map_scalar (fv_mapz.F90:1199-1290: scalar_profile) / map1_ppm (:1293-1383: cs_profile) for kn = km, all rows of the resident
+// tiles at once: one field (isd:ied, jsd:jed, km) per tile, remapped in place from the resident Lagrangian pe onto
+// pe2 = ak + bk*pe(km+1) (the target grid Lagrangian_to_Eulerian builds, :263-272).  kord <= 7 takes ppm_profile in both.
+// These are the callers through which the reference reaches cs_profile (pt, w, delz, u, v: fv_mapz.F90:393-436, 610-660).
+template <class T> struct MapFieldParams {
+  T* q;           // (isd:ied, jsd:jed, km) tile-major, in/out
+  const T* qs;    // (isd:ied, jsd:jed) tile-major bottom boundary value, read for iv = -2 only (may be null otherwise)
+  const T* pe;    // (is-1:ie+1, km+1, js-1:je+1) tile-major
+  const T *ak, *bk;
+  T ptop, q_min;
+  int n, km, ntiles, iv, kord, use_cs;
+};
+template <class T, int KM> __global__ void __launch_bounds__(64) k_map_field(const MapFieldParams<T> p) {
+  const int n = p.n, km = p.km;
+  const long nd = n + 6, plane = nd * nd;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (c >= n * n) return;
+  const int i = c % n + 1, j = c / n + 1;
+  ColWork<T, KM> w;
+  const long pe_ld1 = n + 2, pe_ld2 = pe_ld1 * (km + 1);
+  const T* pe = p.pe + (long)t * pe_ld2 * (n + 2) + (long)i + (long)j * pe_ld2;
+  for (int k = 1; k <= km + 1; ++k) w.pe1[k] = pe[(long)(k - 1) * pe_ld1];
+  const T ps = w.pe1[km + 1];
+  w.pe2[1] = p.ptop;
+  w.pe2[km + 1] = ps;
+  for (int k = 2; k <= km; ++k) w.pe2[k] = p.ak[k - 1] + p.bk[k - 1] * ps;
+  const long col = (long)(j + 2) * nd + (i + 2);
+  T* q = p.q + (long)t * plane * km + col;
+  for (int k = 1; k <= km; ++k) {
+    w.dp2[k] = w.pe2[k + 1] - w.pe2[k];
+    w.dp1[k] = w.pe1[k + 1] - w.pe1[k];
+    w.a1[k] = q[(long)(k - 1) * plane];
+  }
+  const T qs = (p.iv == -2 && p.qs) ? p.qs[(long)t * plane + col] : T(0);
+  if (p.kord > 7) {
+    if (p.use_cs)
+      profile_col<T, KM, false>(w, km, p.iv, p.kord, T(0), qs);
+    else
+      profile_col<T, KM, true>(w, km, p.iv, p.kord, p.q_min, qs);
+  } else {
+    ppm_profile_col<T, KM>(w, km, p.iv, p.kord);
+  }
+  map_col<T, KM, false>(w, km);
+  for (int k = 1; k <= km; ++k) q[(long)(k - 1) * plane] = w.q2[k];
 }
 
 }  // namespace fv3t

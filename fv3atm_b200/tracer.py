@@ -108,6 +108,16 @@ class TracerContext:
                                        int(j), int(i1), int(i2), int(isd), int(ied), int(jsd), int(jed), self._ct(q_min),
                                        int(bool(fill))))
 
+    def map_field(self, q, iv, kord, q_min=0.0, qs=None, use_cs=False):
+        """map_scalar (use_cs = False: scalar_profile) / map1_ppm (use_cs = True: cs_profile) of ONE scalar field
+        q [nt, npz, n+6, n+6] for every row, in place, from the resident pe onto ak + bk*ps (fv3t_*_map_field)."""
+        assert q.dtype == self.dtype and q.flags["C_CONTIGUOUS"]
+        qsp = None
+        if qs is not None:
+            qs = np.ascontiguousarray(qs, dtype=self.dtype)
+            qsp = L.ptr(qs)
+        L.check(self._f("map_field")(self._h, L.ptr(q), qsp, int(iv), int(kord), self._ct(q_min), int(bool(use_cs))))
+
     # ---- device-resident operation -------------------------------------------------------------------
     def upload(self, field: str, host: np.ndarray, nq: int | None = None):
         host = np.ascontiguousarray(host, dtype=self.dtype)

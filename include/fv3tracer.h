@@ -108,6 +108,19 @@ int fv3t_device_count(void);
                              const int* kord, int j, int i1, int i2, int isd, int ied, int jsd, int jed, REAL q_min,   \
                              int fill);                                                                                 \
                                                                                                                         \
+  /* map_scalar(km, pe1, q1, qs, kn, pe2, q2, i1, i2, j, ibeg, iend, jbeg, jend, iv, kord, q_min)  ACS/model/fv_mapz.F90:1199-1290  \
+     map1_ppm  (km, pe1, q1, qs, kn, pe2, q2, i1, i2, j, ibeg, iend, jbeg, jend, iv, kord)         ACS/model/fv_mapz.F90:1293-1383  \
+     for kn = km and all rows js..je of the resident tiles at once (the j loop of Lagrangian_to_Eulerian hoisted, as for the        \
+     tracers): ONE scalar field q (isd:ied, jsd:jed, km) per tile is remapped in place from the resident Lagrangian pe              \
+     (fv3t_*_upload(FV3T_PE)) onto pe2 = ak + bk*pe(km+1) (fv3t_*_set_vertical; fv_mapz.F90:263-272).  map_scalar builds the        \
+     sub-grid profile with scalar_profile (:1691-2096), map1_ppm with cs_profile (:2098-2498) -- the routine through which the       \
+     reference remaps pt, w, delz, u, v (:393-436, 610-660) -- and both with ppm_profile for kord <= 7.  iv: 0 positive definite,    \
+     1 others, -1 winds, 2 (top layer flat), -2 (bottom interface value qs (isd:ied, jsd:jed) given; qs may be NULL otherwise).      \
+     fv3t_*_map_field is the common entry (use_cs selects the profile).  The reference's own operation order, bit for bit. */        \
+  int fv3t_##P##_map_scalar(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord, REAL q_min);                       \
+  int fv3t_##P##_map1_ppm(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord);                                     \
+  int fv3t_##P##_map_field(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord, REAL q_min, int use_cs);            \
+                                                                                                                        \
   /* tracer_2d immediately followed by the tracer remap (they are consecutive in ACS/model/fv_dynamics.F90:686-760), host    \
      arrays in and out, as ONE call: same arguments, same post-state as fv3t_*_tracer_2d + fv3t_*_remap_tracers (q, delp;     \
      dp1, cx, cy, mfx, mfy when nsplt /= 1).  Tracers are independent on this path, so they are pipelined one by one:         \
@@ -142,6 +155,10 @@ int fv3t_device_count(void);
   int fv3t_##P##_halo_local(fv3t_ctx* ctx, int it);                                                                     \
   int fv3t_##P##_halo_pack(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* dev_buf);                             \
   int fv3t_##P##_halo_unpack(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* dev_buf);                     \
+  /* the same with HOST buffers (3*(npx-1)*npz*nq elements): for a host whose MPI is not CUDA-aware -- the strip is packed on  \
+     the device, copied out, exchanged by the host (mpp_send / mpp_recv in the Fortran shim), copied in and scattered */        \
+  int fv3t_##P##_halo_pack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* host_buf);                        \
+  int fv3t_##P##_halo_unpack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* host_buf);                \
   int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac);                                      \
   int fv3t_##P##_tracer_2d_finish(fv3t_ctx* ctx);
 

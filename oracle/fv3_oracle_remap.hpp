@@ -632,15 +632,17 @@ static void mapn_tracer_col(int nq, int km, const T* pe1, const T* pe2, const T*
   if (fill) fillz_col<T>(km, nq, q2, dp2, w.dm);
 }
 
-// map1_q2 (fv_mapz.F90:1502-1592) for one column: a4(1,k) holds q1; q2out(k) 1-based
+// map1_q2 (fv_mapz.F90:1502-1592) for one column: a4(1,k) holds q1; q2out(k) 1-based.  The same body serves map_scalar
+// (:1199-1290: scalar_profile with the bottom value qs) and map1_ppm (:1293-1383: cs_profile, `scalar` = false): the three
+// reference routines differ only in the profile they call and in dp2 being passed (map1_q2) or formed as pe2(k+1)-pe2(k).
 template <class T>
 static void map1_q2_col(int km, const T* pe1, ColA4<T>& q4, int kn, const T* pe2, T* q2out, const T* dp2, int iv, int kord,
-                        T q_min, RemapScratch<T>& w) {
+                        T q_min, RemapScratch<T>& w, bool scalar = true, T qs = T(0)) {
   const T r3 = MapConst<T>::r3, r23 = MapConst<T>::r23;
   T* dp1 = w.dp1.data();
   for (int k = 1; k <= km; ++k) dp1[k] = pe1[k + 1] - pe1[k];
   if (kord > 7)
-    cs_profile_col<T>(true, T(0), q4, dp1, km, iv, kord, q_min, w.prof);
+    cs_profile_col<T>(scalar, qs, q4, dp1, km, iv, kord, q_min, w.prof);
   else
     ppm_profile_col<T>(q4, dp1, km, iv, kord, w.prof);
   int k0 = 1;

@@ -151,6 +151,23 @@ void c_map_col(int which, int km, int nq, const T* pe1, const T* pe2, T* q, cons
   }
 }
 
+// map_scalar (use_cs = 0, fv_mapz.F90:1199-1290) / map1_ppm (use_cs = 1, :1293-1383) for one column, kn = km
+template <class T> void c_map_field_col(int use_cs, int km, const T* pe1, const T* pe2, T* q, int iv, int kord, T q_min, T qs) {
+  RemapScratch<T> w;
+  w.size(km, 1);
+  std::vector<T> p1(km + 3), p2(km + 3), dp2(km + 3), q2(km + 2);
+  for (int k = 1; k <= km + 1; ++k) {
+    p1[k] = pe1[k - 1];
+    p2[k] = pe2[k - 1];
+  }
+  for (int k = 1; k <= km; ++k) {
+    dp2[k] = p2[k + 1] - p2[k];
+    w.a4[0](1, k) = q[k - 1];
+  }
+  map1_q2_col<T>(km, p1.data(), w.a4[0], km, p2.data(), q2.data(), dp2.data(), iv, kord, q_min, w, use_cs == 0, qs);
+  for (int k = 1; k <= km; ++k) q[k - 1] = q2[k];
+}
+
 }  // namespace
 
 #define ORC_API(T, S)                                                                                                          \
@@ -190,6 +207,10 @@ void c_map_col(int which, int km, int nq, const T* pe1, const T* pe2, T* q, cons
   extern "C" void orc_##S##_map_col(int which, int km, int nq, const T* pe1, const T* pe2, T* q, const int* kord, T q_min,  \
                                       int fill) {                                                                              \
     c_map_col<T>(which, km, nq, pe1, pe2, q, kord, q_min, fill);                                                               \
+  }                                                                                                                            \
+  extern "C" void orc_##S##_map_field_col(int use_cs, int km, const T* pe1, const T* pe2, T* q, int iv, int kord, T q_min,    \
+                                            T qs) {                                                                            \
+    c_map_field_col<T>(use_cs, km, pe1, pe2, q, iv, kord, q_min, qs);                                                          \
   }
 
 ORC_API(float, f32)

@@ -214,6 +214,29 @@ int main(void) {
   OK(fv3t_neighbor(ctx, 1, 1, &nt, &ne, &rot));
   CHECK(nt >= 1 && nt <= 6 && ne >= 0 && ne <= 3, "neighbour table");
   CHECK(fv3t_neighbor(ctx, 7, 0, &nt, &ne, &rot) != 0, "bad tile is an error");
+  {
+    /* host-staged strips: what tile 1 sends across its edge 1 is exactly what halo_local copies into the neighbour's halo */
+    const size_t nel = fv3t_halo_strip_elems(ctx);
+    double* strip = (double*)malloc(nel * sizeof(double));
+    OK(fv3t_neighbor(ctx, 1, 1, &nt, &ne, &rot));
+    OK(fv3t_f64_upload(ctx, FV3T_Q, q0, NQ));
+    OK(fv3t_f64_halo_local(ctx, 1));
+    double* qh = (double*)malloc(nq_el * sizeof(double));
+    OK(fv3t_f64_download(ctx, FV3T_Q, qh, NQ));
+    OK(fv3t_f64_upload(ctx, FV3T_Q, q0, NQ));
+    OK(fv3t_f64_halo_pack_host(ctx, 1, 0, 1, strip));
+    OK(fv3t_f64_halo_unpack_host(ctx, 1, nt - 1, ne, strip));
+    double* qs = (double*)malloc(nq_el * sizeof(double));
+    OK(fv3t_f64_download(ctx, FV3T_Q, qs, NQ));
+    size_t changed = 0, wrong = 0;
+    for (size_t e = 0; e < nq_el; ++e)
+      if (qs[e] != q0[e]) {
+        ++changed;
+        wrong += qs[e] != qh[e];
+      }
+    CHECK(changed > 0 && wrong == 0, "pack_host -> unpack_host fills the neighbour's edge halo like halo_local");
+    free(strip), free(qh), free(qs);
+  }
   /* tracer_step: both calls in one, host arrays in and out */
   memcpy(q, q0, nq_el * sizeof(double));
   OK(fv3t_f64_tracer_step(ctx, q, dp1, mfx, mfy, cx, cy, pe, ak, bk, ptop, delp, NQ, 8, 0, 1.0, kord, 1, &nsplt));

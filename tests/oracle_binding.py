@@ -172,3 +172,14 @@ def map_col(which, pe1, pe2, q, kord, q_min=0.0, fill=False):
     getattr(lib(), f"orc_{s}_map_col")(int(which), int(km), int(nq), _p(pe1), _p(pe2), _p(out), _p(kord), ct(q_min),
                                       int(bool(fill)))
     return out
+
+
+def map_field_col(use_cs, pe1, pe2, q, iv, kord, q_min=0.0, qs=0.0):
+    """map_scalar (use_cs = False: scalar_profile) / map1_ppm (use_cs = True: cs_profile) for one column q [km], kn = km"""
+    s, ct = _sfx(q.dtype)
+    km = q.shape[0]
+    out = np.array(q, copy=True, order="C")
+    pe1 = np.ascontiguousarray(pe1, dtype=q.dtype)
+    pe2 = np.ascontiguousarray(pe2, dtype=q.dtype)
+    getattr(lib(), f"orc_{s}_map_field_col")(int(bool(use_cs)), int(km), _p(pe1), _p(pe2), _p(out), int(iv), int(kord), ct(q_min), ct(qs))
+    return out

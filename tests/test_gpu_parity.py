@@ -432,3 +432,41 @@ def test_mapn_tracer_consumes_the_callers_target_grid(oracle, case_factory, nq, 
             assert np.array_equal(q1[:, :, j + 2, i + 3], want), (j, i)
     untouched = [j for j in range(1, n + 1) if j not in rows]
     assert np.array_equal(q1[:, :, [j + 2 for j in untouched]], q_in[:, :, [j + 2 for j in untouched]])
+
+
+# ---- cs_profile on the GPU: map1_ppm / map_scalar (the rest of the vertical remap reaches cs_profile through them) ----------------
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("use_cs", [True, False])
+@pytest.mark.parametrize("kord", [9, 11, 15, 10, 12, 13, 14, 16, 8, 17, 4, 6, 7])
+def test_map1_ppm_and_map_scalar_against_the_oracle(oracle, case_factory, kord, use_cs, dtype):
+    """fv3t_*_map1_ppm (cs_profile, fv_mapz.F90:2098-2498 -- including its own kord 9 / 11 / 15 branches and the
+    6*a1 - 3*(a2+a3) rounding of :2324) and fv3t_*_map_scalar (scalar_profile with q_min) for iv = 0, 1, -1 and -2 (bottom value
+    given): bit-identical to the oracle's restatement, column by column."""
+    import oracle_binding as ob
+    case = case_factory(12, 32, 9, dtype)
+    n, km = case.n, case.npz
+    ctx = TracerContext(n + 1, km, 1, case.metrics(), dtype=case.dtype)
+    ctx.upload("pe", case.pe)
+    ctx.set_vertical(case.ak, case.bk, case.ptop)
+    rng = np.random.default_rng(kord)
+    fields = {0: np.ascontiguousarray(case.q[:, 4]),                                           # sparse random positive (iv = 0)
+              1: np.ascontiguousarray(case.q[:, 5] * 30 + 280),                                # temperature-like (iv = 1)
+              -1: np.ascontiguousarray(case.q[:, 5] * 40),                                     # signed, wind-like (iv = -1)
+              -2: np.ascontiguousarray(case.q[:, 1] * 1e3 + 1)}                                # with a bottom boundary value
+    ak = np.asarray(case.ak, dtype=case.dtype)
+    bk = np.asarray(case.bk, dtype=case.dtype)
+    for iv, f in fields.items():
+        got = f.copy()
+        qs = np.ascontiguousarray(f[:, -1] * case.dtype.type(1.05)) if iv == -2 else None
+        q_min = 0.0 if iv != 0 else 1e-6
+        ctx.map_field(got, iv, kord, q_min=q_min, qs=qs, use_cs=use_cs)
+        for t in (0, 3, 5):
+            for (i, j) in [(1, 1), (n, n), (5, 7), (n, 2), (3, n)]:
+                pe1 = np.ascontiguousarray(case.pe[t, j, :, i])
+                ps = pe1[-1]
+                pe2 = (ak + bk * ps).astype(case.dtype)
+                pe2[0], pe2[-1] = case.dtype.type(case.ptop), ps
+                col = np.ascontiguousarray(f[t, :, j + 2, i + 2])
+                want = ob.map_field_col(use_cs, pe1, pe2, col, iv, kord, q_min=q_min, qs=float(qs[t, j + 2, i + 2]) if qs is not None else 0.0)
+                assert np.array_equal(got[t, :, j + 2, i + 2], want), (iv, t, i, j, np.abs(got[t, :, j + 2, i + 2] - want).max())
+    ctx.close()
