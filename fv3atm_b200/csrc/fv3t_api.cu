@@ -20,6 +20,7 @@
 #include "fv3t_remap.cuh"
 #include "fv3t_remap2.cuh"
 #include "fv3t_fast.h"
+#include "fv3t_deln.cuh"
 
 namespace {
 
@@ -170,6 +171,10 @@ template <class T> struct Impl {
   uint64_t launches = 0;
   std::mutex row_mutex;
   T* row_buf = nullptr;  // staging for the row-granular mapn_tracer entry
+  // tracer damping (deln_flux, fv3t_deln.cuh): fv_grid_type%del6_u / del6_v / da_min, the settings of the current call, scratch
+  T *del6_u = nullptr, *del6_v = nullptr, *dfx2 = nullptr, *dfy2 = nullptr, *dd2 = nullptr;
+  T da_min = T(0), damp_trdm = T(0);
+  int damp_nord = 0;
   T* fld = nullptr;        // device staging of one scalar field (map_scalar / map1_ppm entries), sized like delp
   T* fld_qs = nullptr;     // its bottom boundary values (iv = -2)
   T* strip_buf = nullptr;  // device staging of one packed edge strip (halo_pack_host / halo_unpack_host)
@@ -239,6 +244,7 @@ template <class T> struct Impl {
   int halo_pack(int it, int lt, int edge, T* buf, bool unpack);
   int substep(int it, int hord, T lim_fac);
   int prepare(int hord, bool allow5 = true);
+  int apply_damping(int it, bool mf_scaled);
   int alloc5();
   int finish();
   int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
@@ -368,7 +374,7 @@ template <class T> int Impl<T>::destroy() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
   void* ptrs[] = {q[0], q[1], xfs, yfs, X2, Y2, cab, rrx, rry, X5, Y5, C5, RX5, RY5, MX5, MY5, AREA5, RAREA5, coef4, neg4, P1, GAM, RD1, R2, dp1, mfx, mfy, cx, cy, pe, delp, area, rarea, dx, dy, dxa, dya, sin_sg, ak, bk, cmax_t,
-                  ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf, strip_buf, fld, fld_qs};
+                  ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf, strip_buf, fld, fld_qs, del6_u, del6_v, dfx2, dfy2, dd2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int s = 0; s < 6; ++s)
@@ -670,7 +676,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     else
       CK(fv3t::fast_advect5<T>(p, maps5, hord, nt * npz, stream));
     kend(KC_ADVECT);
-    return 0;
+    return apply_damping(it, false);  // mfx, mfy are scaled by finish() on this path
   }
   if (call_fast) {
     if (!fv3t::fast_hord_ok(hord)) return fail("fv3tracer: hord_tr changed between the sub-steps of one tracer_2d call");
@@ -712,7 +718,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     const int NT = (forced >= 32 && forced <= 256 && forced % 32 == 0) ? forced : 64;
     CK(fv3t::fast_advect3<T>(p, hord, NT, stream));
     kend(KC_ADVECT);
-    return 0;
+    return apply_damping(it, true);
   }
   fv3t::Adv2Params<T> p;
   p.qin = q[(cur + it - 1) & 1];
@@ -752,6 +758,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     default: return fail("fv3tracer: hord_tr = %d is not a scheme of xppm/yppm", hord);
   }
   if (rc) return rc;
+  if ((rc = apply_damping(it, true))) return rc;
   // dp1 <- dp2 between sub-steps (fv_tracer2d.F90:547-553; tests the GLOBAL nsplt)
   if (it != nsplt) {
     dim3 grid(8, nt * npz);
@@ -760,6 +767,58 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     kend(KC_SCALE);
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+// Tracer damping of the first sub-step (fv_tracer2d.F90:487-494, 527-532 -> tp_core.F90:229-234 -> deln_flux :1239-1387), applied
+// to the field the advection kernel has just written; see fv3t_deln.cuh.
+template <class T> int Impl<T>::apply_damping(int it, bool mf_scaled) {
+  if (it != 1 || !(damp_trdm > T(1.e-4))) return 0;
+  if (!del6_u) return fail("fv3tracer: tracer damping needs the damping metrics (fv3t_*_set_damping)");
+  if (nt != 6) return fail("fv3tracer: tracer damping needs all six tiles resident (the dp1 halo is filled locally)");
+  if (damp_nord < 0 || damp_nord > 2) return fail("fv3tracer: nord_tr = %d outside 0..2 (deln_flux needs nord + 1 <= ng halo cells)", damp_nord);
+  const int nd = n + 6;
+  const size_t planes = (size_t)nt * npz;
+  auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+  CK(dalloc((void**)&dfx2, planes * nd * (nd + 1) * sizeof(T)));
+  CK(dalloc((void**)&dfy2, planes * nd * (nd + 1) * sizeof(T)));
+  CK(dalloc((void**)&dd2, planes * nd * nd * sizeof(T)));
+  // mass = dp1 with its edge halos (complete_group_halo_update(dp1_pack), fv_tracer2d.F90:487-494)
+  if (halo_len) {
+    dim3 gh((halo_len + 255) / 256, npz);
+    kbegin();
+    fv3t::k_halo_fill<T><<<gh, 256, 0, stream>>>(dp1, halo_dst, halo_src, halo_len, n, npz, 1, ksplt_d, 1);
+    kend(KC_HALO);
+  }
+  const T damp = (T)std::pow((double)(damp_trdm * da_min), (double)(damp_nord + 1));
+  const T* qin = q[(cur + it - 1) & 1];
+  T* qout = q[(cur + it) & 1];
+  dim3 grid(64, (unsigned)planes);
+  for (int iq = 0; iq < nq_cur; ++iq) {
+    fv3t::DelnParams<T> p{qin + (size_t)iq * sz_c(), dfx2, dfy2, dd2, del6_u, del6_v, rarea, n, npz, damp_nord, damp_nord, 1,
+                          (long)sz_q(nq_cur)};
+    kbegin();
+    fv3t::k_deln_flux<T><<<grid, 256, 0, stream>>>(p);
+    kend(KC_ADVECT);
+    for (int s = 1; s <= damp_nord; ++s) {
+      p.nt = damp_nord - s;
+      p.first = 0;
+      p.src = dd2;
+      p.src_tile_stride = (long)sz_c();
+      kbegin();
+      fv3t::k_deln_div<T><<<grid, 256, 0, stream>>>(p);
+      kend(KC_ADVECT);
+      kbegin();
+      fv3t::k_deln_flux<T><<<grid, 256, 0, stream>>>(p);
+      kend(KC_ADVECT);
+    }
+    fv3t::DelnApplyParams<T> a{qout + (size_t)iq * sz_c(), dfx2, dfy2, dp1, mfx, mfy, rarea, ksplt_d, (long)sz_q(nq_cur), n, npz,
+                               mf_scaled ? 1 : 0, damp};
+    kbegin();
+    fv3t::k_deln_apply<T><<<grid, 256, 0, stream>>>(a);
+    kend(KC_ADVECT);
+  }
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1220,8 +1279,16 @@ extern "C" int fv3t_device_count(void) {
                                       int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out,            \
                                       int* ksplt_out) {                                                                        \
     NEED(ctx, P);                                                                                                              \
-    (void)nord_tr;                                                                                                             \
-    if (trdm > REAL(1.e-4)) return fail("fv3tracer: tracer del-2 damping (trdm2 > 1e-4, deln_flux) is not supported");        \
+    if (trdm > REAL(1.e-4) && !I->del6_u)                                                                                      \
+      return fail("fv3tracer: tracer damping (trdm2 > 1e-4, deln_flux) needs the damping metrics: call fv3t_*_set_damping first"); \
+    const REAL trdm_keep = I->damp_trdm;                                                                                       \
+    const int nord_keep = I->damp_nord;                                                                                        \
+    I->damp_trdm = trdm;                                                                                                       \
+    I->damp_nord = nord_tr;                                                                                                    \
+    struct Restore {                                                                                                           \
+      Impl<REAL>* i; REAL t; int n;                                                                                            \
+      ~Restore() { i->damp_trdm = t; i->damp_nord = n; }                                                                       \
+    } restore{I, trdm_keep, nord_keep};                                                                                        \
     int rc;                                                                                                                    \
     if ((rc = I->upload(FV3T_Q, q, nq))) return rc;                                                                            \
     if ((rc = I->upload(FV3T_DP1, dp1, nq))) return rc;                                                                        \
@@ -1239,6 +1306,26 @@ extern "C" int fv3t_device_count(void) {
       if ((rc = I->download(FV3T_CX, cx, nq))) return rc;                                                                      \
       if ((rc = I->download(FV3T_CY, cy, nq))) return rc;                                                                      \
     }                                                                                                                          \
+    return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_set_damping(fv3t_ctx* ctx, const REAL* del6_u, const REAL* del6_v, REAL da_min, int nord_tr,      \
+                                        REAL trdm) {                                                                           \
+    NEED(ctx, P);                                                                                                              \
+    CK(cudaSetDevice(I->device));                                                                                              \
+    if (del6_u && del6_v) {                                                                                                    \
+      const size_t ne = (size_t)I->nt * (I->n + 6) * (I->n + 7);                                                               \
+      if (!I->del6_u) CK(cudaMalloc((void**)&I->del6_u, ne * sizeof(REAL)));                                                   \
+      if (!I->del6_v) CK(cudaMalloc((void**)&I->del6_v, ne * sizeof(REAL)));                                                   \
+      CK(cudaMemcpyAsync(I->del6_u, del6_u, ne * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                            \
+      CK(cudaMemcpyAsync(I->del6_v, del6_v, ne * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                            \
+      CK(cudaStreamSynchronize(I->stream));                                                                                    \
+      I->da_min = da_min;                                                                                                      \
+    } else if (trdm > REAL(1.e-4) && !I->del6_u) {                                                                             \
+      return fail("fv3tracer: set_damping: del6_u / del6_v have never been provided");                                        \
+    }                                                                                                                          \
+    if (nord_tr < 0 || nord_tr > 2) return fail("fv3tracer: nord_tr = %d outside 0..2", nord_tr);                             \
+    I->damp_nord = nord_tr;                                                                                                    \
+    I->damp_trdm = trdm;                                                                                                       \
     return 0;                                                                                                                  \
   }                                                                                                                            \
   extern "C" int fv3t_##P##_tracer_2d_1L(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,  \

@@ -330,6 +330,29 @@ class Grid:
                 for k in ("area", "rarea", "dx", "dy", "dxa", "dya", "sin_sg")}
 
 
+def damping_metrics(grid: "Grid"):
+    """``del6_u (isd:ied, jsd:jed+1)``, ``del6_v (isd:ied+1, jsd:jed)`` and ``da_min`` of ``fv_grid_type`` (fv_arrays.F90:124,183),
+    read by ``deln_flux`` only (tracer damping, off by default).  Form of fv_grid_utils.F90:799-819 -- ``del6_v = sin * dy / dxc``,
+    ``del6_u = sin * dx / dyc`` with the face sine taken from the two adjacent sub-cell values -- with the C-grid distances
+    ``dxc, dyc`` (which this synthetic grid does not carry) replaced by the mean of the two adjacent A-grid widths.  Inputs of the
+    path like every other metric: the oracle and the library are handed the same arrays.  Returns ([6, nd+1, nd], [6, nd, nd+1], da_min)."""
+    nd = grid.n + 2 * NG
+    ss = np.nan_to_num(grid.sin_sg, nan=1.0)
+    dxa, dya = np.nan_to_num(grid.dxa, nan=1.0), np.nan_to_num(grid.dya, nan=1.0)
+    del6_v = np.zeros((6, nd, nd + 1))
+    del6_u = np.zeros((6, nd + 1, nd))
+    # x-faces i = isd..ied+1: cells i-1 (east value, position 3) and i (west value, position 1); one-sided at the array ends
+    sin_w = np.concatenate([ss[:, 0], ss[:, 0, :, -1:]], axis=2)           # position 1 of cell i
+    sin_e = np.concatenate([ss[:, 2, :, :1], ss[:, 2]], axis=2)            # position 3 of cell i-1
+    dxc = 0.5 * (np.concatenate([dxa[:, :, :1], dxa], axis=2) + np.concatenate([dxa, dxa[:, :, -1:]], axis=2))
+    del6_v[:] = 0.5 * (sin_w + sin_e) * np.nan_to_num(grid.dy, nan=1.0) / dxc
+    sin_s = np.concatenate([ss[:, 1], ss[:, 1, -1:, :]], axis=1)           # position 2 of cell j
+    sin_n = np.concatenate([ss[:, 3, :1, :], ss[:, 3]], axis=1)            # position 4 of cell j-1
+    dyc = 0.5 * (np.concatenate([dya[:, :1, :], dya], axis=1) + np.concatenate([dya, dya[:, -1:, :]], axis=1))
+    del6_u[:] = 0.5 * (sin_s + sin_n) * np.nan_to_num(grid.dx, nan=1.0) / dyc
+    return del6_u, del6_v, float(grid.da_min)
+
+
 def extended_corner_points(n: int, ng: int = NG) -> np.ndarray:
     """Corner points on ``(1-ng : n+1+ng)^2`` per tile: own points inside, the neighbouring tile's own
     points in the four edge halos (what the halo update of ``grid`` delivers, fv_grid_tools.F90:886-890).

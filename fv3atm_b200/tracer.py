@@ -66,6 +66,13 @@ class TracerContext:
                                      C.byref(nsplt), L.ptr(ksplt)))
         return nsplt.value, ksplt
 
+    def set_damping(self, del6_u, del6_v, da_min, nord_tr=0, trdm=0.0):
+        """fv_grid_type%del6_u / del6_v / da_min for deln_flux (tracer damping) and the settings of the resident entries."""
+        d6u = np.ascontiguousarray(del6_u, dtype=self.dtype) if del6_u is not None else None
+        d6v = np.ascontiguousarray(del6_v, dtype=self.dtype) if del6_v is not None else None
+        L.check(self._f("set_damping")(self._h, L.ptr(d6u) if d6u is not None else None, L.ptr(d6v) if d6v is not None else None,
+                                       self._ct(da_min), int(nord_tr), self._ct(trdm)))
+
     def tracer_2d_1L(self, q, dp1, mfx, mfy, cx, cy, hord, nord_tr=0, trdm=0.0, lim_fac=1.0):
         """tracer_2d_1L (fv_tracer2d.F90:92-321, the z_tracer variant): same q / cx / cy / mfx / mfy post-state as tracer_2d, dp1
         advanced only between a level's own sub-steps.  Returns (max over k of the per-level sub-step count, the counts)."""

@@ -79,10 +79,18 @@ int fv3t_device_count(void);
      Host arrays in, host arrays out; reproduces the reference's side effects: q updated on the compute domain,       \
      cx, cy, mfx, mfy scaled by 1/ksplt(k) when nsplt /= 1 (:463-481), dp1 advanced between sub-steps (:549).         \
      The halo update of q that the reference completes at :499 is performed internally for the resident tiles          \
-     (requires ntiles == 6).  nord_tr/trdm: only trdm <= 1e-4 (no tracer damping) is supported -> error otherwise.     \
+     (requires ntiles == 6).  nord_tr / trdm: tracer damping (deln_flux on the first sub-step, :487-494, 527-532) when     \
+     trdm > 1e-4; needs the damping metrics of fv3t_*_set_damping, nord_tr in 0..2.                                    \
      nsplt_out / ksplt_out[npz] (optional) return the sub-step counts (:441,:457). */                                  \
   int fv3t_##P##_tracer_2d(fv3t_ctx* ctx, REAL* q, REAL* dp1, REAL* mfx, REAL* mfy, REAL* cx, REAL* cy, int nq,         \
                            int hord, int q_split, int nord_tr, REAL trdm, REAL lim_fac, int* nsplt_out, int* ksplt_out); \
+                                                                                                                        \
+  /* Tracer damping = deln_flux (ACS/model/tp_core.F90:1239-1387) as fv_tp_2d calls it for tracers (:229-234): the members of     \
+     fv_grid_type it reads, del6_u (isd:ied, jsd:jed+1), del6_v (isd:ied+1, jsd:jed) (fv_arrays.F90:124) and da_min (:183),      \
+     tile-major, plus the settings used by the device-resident entries (fv3t_*_tracer_2d takes nord_tr / trdm per call).          \
+     del6_u = del6_v = NULL keeps the metrics and only changes the settings.  trdm <= 1e-4 switches the damping off.            \
+     The damping fluxes are applied as a correction of the advected field: same terms as the reference, to rounding. */          \
+  int fv3t_##P##_set_damping(fv3t_ctx* ctx, const REAL* del6_u, const REAL* del6_v, REAL da_min, int nord_tr, REAL trdm);   \
                                                                                                                         \
   /* tracer_2d_1L(q, dp1, mfx, mfy, cx, cy, gridstruct, bd, domain, npx, npy, npz, nq, hord, q_split, dt, id_divg, q_pack,        \
                   dp1_pack, nord_tr, trdm, lim_fac)                  ACS/model/fv_tracer2d.F90:92-113, called for z_tracer        \

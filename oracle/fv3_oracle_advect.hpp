@@ -458,6 +458,8 @@ struct Bounds {
 // The fields of fv_grid_type read on the path, one tile, `real` precision.
 template <class T> struct GridT {
   const T *area, *rarea, *dx, *dy, *dxa, *dya, *sin_sg;  // sin_sg: (isd:ied, jsd:jed, 5)
+  const T *del6_u = nullptr, *del6_v = nullptr;          // (isd:ied, jsd:jed+1) / (isd:ied+1, jsd:jed), fv_arrays.F90:124; deln_flux only
+  T da_min = T(0);                                       // fv_arrays.F90:183
   bool bounded_domain = false;
   int grid_type = 0;
   bool sw_corner = true, se_corner = true, nw_corner = true, ne_corner = true;
@@ -542,10 +544,51 @@ template <class T> struct Tp2dScratch {
 
 // fv_tp_2d (tp_core.F90:110-249).  mfx/mfy present -> tracer branch; nullptr -> xfx/yfx branch.
 // (deln_flux, the optional tracer damping, is not restated: trdm2 = 0 in every configuration in scope.)
+// deln_flux (tp_core.F90:1239-1387), the form with `mass` present and USE_SG undefined (CMake default): del-(2 nord + 2) damping
+// fluxes of the cell means, mass weighted, added to fx, fy.  q is ghosted on input and carries the dir = 1 corner view that
+// fv_tp_2d left in it (tp_core.F90:189).
+template <class T>
+static void deln_flux(int nord, int npx, int npy, T damp, V2<const T> q, V2<T> fx, V2<T> fy, const GridT<T>& g, const Bounds& bd,
+                      const T* mass_p) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const long nxd = ied - isd + 1, nyd = jed - jsd + 1;
+  std::vector<T> fx2v((size_t)(nxd + 1) * nyd, T(0)), fy2v((size_t)nxd * (nyd + 1), T(0)), d2v((size_t)nxd * nyd, T(0));
+  V2<T> fx2{fx2v.data(), isd, jsd, nxd + 1}, fy2{fy2v.data(), isd, jsd, nxd}, d2{d2v.data(), isd, jsd, nxd};
+  V2<const T> del6_v{g.del6_v, isd, jsd, nxd + 1}, del6_u{g.del6_u, isd, jsd, nxd}, rarea{g.rarea, isd, jsd, nxd};
+  V2<const T> mass{mass_p, isd, jsd, nxd};
+  const int i1 = is - 1 - nord, i2 = ie + 1 + nord, j1 = js - 1 - nord, j2 = je + 1 + nord;
+  for (int j = j1; j <= j2; ++j)
+    for (int i = i1; i <= i2; ++i) d2(i, j) = q(i, j);  // `mass` present: damp is applied with the mass weighting below
+  if (nord > 0) copy_corners(d2, npx, npy, 1, bd, g);
+  for (int j = js - nord; j <= je + nord; ++j)
+    for (int i = is - nord; i <= ie + nord + 1; ++i) fx2(i, j) = del6_v(i, j) * (d2(i - 1, j) - d2(i, j));
+  if (nord > 0) copy_corners(d2, npx, npy, 2, bd, g);
+  for (int j = js - nord; j <= je + nord + 1; ++j)
+    for (int i = is - nord; i <= ie + nord; ++i) fy2(i, j) = del6_u(i, j) * (d2(i, j - 1) - d2(i, j));
+  for (int n = 1; n <= nord; ++n) {
+    const int nt = nord - n;
+    for (int j = js - nt - 1; j <= je + nt + 1; ++j)
+      for (int i = is - nt - 1; i <= ie + nt + 1; ++i)
+        d2(i, j) = (fx2(i, j) - fx2(i + 1, j) + fy2(i, j) - fy2(i, j + 1)) * rarea(i, j);
+    copy_corners(d2, npx, npy, 1, bd, g);
+    for (int j = js - nt; j <= je + nt; ++j)
+      for (int i = is - nt; i <= ie + nt + 1; ++i) fx2(i, j) = del6_v(i, j) * (d2(i, j) - d2(i - 1, j));
+    copy_corners(d2, npx, npy, 2, bd, g);
+    for (int j = js - nt; j <= je + nt + 1; ++j)
+      for (int i = is - nt; i <= ie + nt; ++i) fy2(i, j) = del6_u(i, j) * (d2(i, j) - d2(i, j - 1));
+  }
+  const T damp2 = T(0.5) * damp;
+  for (int j = js; j <= je; ++j)
+    for (int i = is; i <= ie + 1; ++i) fx(i, j) = fx(i, j) + damp2 * (mass(i - 1, j) + mass(i, j)) * fx2(i, j);
+  for (int j = js; j <= je + 1; ++j)
+    for (int i = is; i <= ie; ++i) fy(i, j) = fy(i, j) + damp2 * (mass(i, j - 1) + mass(i, j)) * fy2(i, j);
+}
+
 template <class T>
 static void fv_tp_2d(V2<T> q, V2<const T> crx, V2<const T> cry, int npx, int npy, int hord, V2<T> fx, V2<T> fy,
                      V2<const T> xfx, V2<const T> yfx, const GridT<T>& g, const Bounds& bd, V2<const T> ra_x,
-                     V2<const T> ra_y, T lim_fac, const T* mfx_p, const T* mfy_p, Tp2dScratch<T>& w) {
+                     V2<const T> ra_y, T lim_fac, const T* mfx_p, const T* mfy_p, Tp2dScratch<T>& w, const T* mass_p = nullptr,
+                     int nord = 0, T damp_c = T(0)) {
   const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
   const long nxd = ied - isd + 1, nx = ie - is + 1;
   V2<T> q_i{w.q_i.data(), isd, js, nxd};
@@ -586,6 +629,10 @@ static void fv_tp_2d(V2<T> q, V2<const T> crx, V2<const T> cry, int npx, int npy
       for (int i = is; i <= ie + 1; ++i) fx(i, j) = T(0.5) * (fx(i, j) + fx2(i, j)) * mfx(i, j);
     for (int j = js; j <= je + 1; ++j)
       for (int i = is; i <= ie; ++i) fy(i, j) = T(0.5) * (fy(i, j) + fy2(i, j)) * mfy(i, j);
+    if (mass_p && damp_c > T(1.e-4)) {  // tp_core.F90:229-234
+      const T damp = std::pow(damp_c * g.da_min, (T)(nord + 1));
+      deln_flux<T>(nord, npx, npy, damp, cv(q), fx, fy, g, bd, mass_p);
+    }
   } else {
     for (int j = js; j <= je; ++j)
       for (int i = is; i <= ie + 1; ++i) fx(i, j) = T(0.5) * (fx(i, j) + fx2(i, j)) * xfx(i, j);
@@ -626,7 +673,7 @@ template <class T> static void halo_update(const Mosaic<T>& m) {
 
 template <class T>
 static void tracer_2d_mosaic(const Mosaic<T>& m, int hord, int q_split, T lim_fac, int* nsplt_out, int* ksplt_out,
-                             T* cmax_out) {
+                             T* cmax_out, int nord_tr = 0, T trdm = T(0)) {
   const Bounds bd = Bounds::tile(m.n);
   const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
   const int npx = bd.npx, npy = bd.npy, npz = m.npz, nq = m.nq;
@@ -722,6 +769,15 @@ static void tracer_2d_mosaic(const Mosaic<T>& m, int hord, int q_split, T lim_fa
   if (ksplt_out) std::memcpy(ksplt_out, ksplt.data(), sizeof(int) * npz);
   if (cmax_out) std::memcpy(cmax_out, cmax.data(), sizeof(T) * npz);
 
+  // ---- tracer damping: the edge halo of dp1 (complete_group_halo_update(dp1_pack), :487-494)
+  if (trdm > T(1.e-4)) {
+    const int64_t plane = sz_q2;
+    for (int64_t pl = 0; pl < npz; ++pl)
+      for (int64_t e = 0; e < m.halo_len; ++e) {
+        const int64_t d = m.halo_dst[e], s = m.halo_src[e];
+        m.dp1[(d / plane) * plane * npz + pl * plane + d % plane] = m.dp1[(s / plane) * plane * npz + pl * plane + s % plane];
+      }
+  }
   // ---- step E: sub-cycled transport (:496-566)
   for (int it = 1; it <= nsplt; ++it) {
     halo_update(m);  // complete_group_halo_update(q_pack)
@@ -756,8 +812,12 @@ static void tracer_2d_mosaic(const Mosaic<T>& m, int hord, int q_split, T lim_fa
               for (int i = isd; i <= ied; ++i) ra_y(i, j) = area(i, j) + yfx(i, j) - yfx(i, j + 1);
             for (int iq = 1; iq <= nq; ++iq) {
               V2<T> q{m.q + (size_t)t * sz_q2 * npz * nq + ((size_t)(iq - 1) * npz + (k - 1)) * sz_q2, isd, jsd, nxd};
-              fv_tp_2d<T>(q, cx, cy, npx, npy, hord, fx, fy, xfx, yfx, g, bd, V2<const T>{ra_x.p, is, jsd, nx},
-                          V2<const T>{ra_y.p, isd, js, nxd}, lim_fac, mfx.p, mfy.p, w);
+              if (it == 1 && trdm > T(1.e-4))  // :527-532: damping with the first sub-step only
+                fv_tp_2d<T>(q, cx, cy, npx, npy, hord, fx, fy, xfx, yfx, g, bd, V2<const T>{ra_x.p, is, jsd, nx},
+                            V2<const T>{ra_y.p, isd, js, nxd}, lim_fac, mfx.p, mfy.p, w, dp1.p, nord_tr, trdm);
+              else
+                fv_tp_2d<T>(q, cx, cy, npx, npy, hord, fx, fy, xfx, yfx, g, bd, V2<const T>{ra_x.p, is, jsd, nx},
+                            V2<const T>{ra_y.p, isd, js, nxd}, lim_fac, mfx.p, mfy.p, w);
               for (int j = js; j <= je; ++j)
                 for (int i = is; i <= ie; ++i)
                   q(i, j) = (q(i, j) * dp1(i, j) + (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1)) * rarea(i, j)) / dp2(i, j);

@@ -24,7 +24,7 @@ template <class T>
 void c_tracer_2d(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area, const T* rarea,
                  const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, const int64_t* halo_dst,
                  const int64_t* halo_src, int64_t halo_len, int hord, int q_split, T lim_fac, int* nsplt_out, int* ksplt_out,
-                 T* cmax_out) {
+                 T* cmax_out, const T* del6_u = nullptr, const T* del6_v = nullptr, T da_min = T(0), int nord_tr = 0, T trdm = T(0)) {
   const long nd = n + 6;
   std::vector<GridT<T>> g(ntiles);
   for (int t = 0; t < ntiles; ++t) {
@@ -35,9 +35,12 @@ void c_tracer_2d(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mf
     g[t].dxa = dxa + (long)t * nd * nd;
     g[t].dya = dya + (long)t * nd * nd;
     g[t].sin_sg = sin_sg + (long)t * nd * nd * 5;
+    if (del6_u) g[t].del6_u = del6_u + (long)t * nd * (nd + 1);
+    if (del6_v) g[t].del6_v = del6_v + (long)t * (nd + 1) * nd;
+    g[t].da_min = da_min;
   }
   Mosaic<T> m{ntiles, n, npz, nq, q, dp1, mfx, mfy, cx, cy, g.data(), halo_dst, halo_src, halo_len};
-  tracer_2d_mosaic<T>(m, hord, q_split, lim_fac, nsplt_out, ksplt_out, cmax_out);
+  tracer_2d_mosaic<T>(m, hord, q_split, lim_fac, nsplt_out, ksplt_out, cmax_out, nord_tr, trdm);
 }
 
 template <class T>
@@ -181,6 +184,15 @@ template <class T> void c_map_field_col(int use_cs, int km, const T* pe1, const 
                                         int hord, int q_split, T lim_fac, int* nsplt_out, int* ksplt_out, T* cmax_out) {      \
     c_tracer_2d<T>(ntiles, n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst, halo_src,    \
                    halo_len, hord, q_split, lim_fac, nsplt_out, ksplt_out, cmax_out);                                          \
+  }                                                                                                                            \
+  extern "C" void orc_##S##_tracer_2d_damp(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy,  \
+                                             const T* area, const T* rarea, const T* dx, const T* dy, const T* dxa,          \
+                                             const T* dya, const T* sin_sg, const int64_t* halo_dst, const int64_t* halo_src, \
+                                             int64_t halo_len, int hord, int q_split, T lim_fac, int* nsplt_out,             \
+                                             int* ksplt_out, T* cmax_out, const T* del6_u, const T* del6_v, T da_min,         \
+                                             int nord_tr, T trdm) {                                                           \
+    c_tracer_2d<T>(ntiles, n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst, halo_src,    \
+                   halo_len, hord, q_split, lim_fac, nsplt_out, ksplt_out, cmax_out, del6_u, del6_v, da_min, nord_tr, trdm);   \
   }                                                                                                                            \
   extern "C" void orc_##S##_tracer_2d_1l(int ntiles, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy,    \
                                            const T* area, const T* rarea, const T* dx, const T* dy, const T* dxa,           \

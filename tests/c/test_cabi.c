@@ -89,8 +89,18 @@ int main(void) {
         }
   OK(fv3t_f64_tracer_2d_1L(ctx, q, dp1, mfx, mfy, cx, cy, NQ, 10, 0, 0, 0.0, 1.0, &nsplt, ksplt));
   CHECK(nsplt == 1, "tracer_2d_1L nsplt");
-  CHECK(fv3t_f64_tracer_2d(ctx, q, dp1, mfx, mfy, cx, cy, NQ, 8, 0, 2, 0.2, 1.0, &nsplt, ksplt) != 0, "tracer damping is documented as unsupported");
-  CHECK(strstr(fv3t_last_error(), "deln_flux") != NULL, "error string names the missing piece");
+  CHECK(fv3t_f64_tracer_2d(ctx, q, dp1, mfx, mfy, cx, cy, NQ, 8, 0, 2, 0.2, 1.0, &nsplt, ksplt) != 0, "tracer damping without its metrics is an error");
+  CHECK(strstr(fv3t_last_error(), "set_damping") != NULL, "error string names the missing call");
+  {
+    /* with the metrics: a horizontally uniform field has no del-n flux, so q must come back unchanged to rounding */
+    double* d6u = filled(6 * (size_t)ND * (ND + 1), 1.0);
+    double* d6v = filled(6 * (size_t)ND * (ND + 1), 1.0);
+    OK(fv3t_f64_set_damping(ctx, d6u, d6v, 1.0, 1, 0.0));
+    double* qu = filled(nq_el, 3.25);
+    OK(fv3t_f64_tracer_2d(ctx, qu, dp1, mfx, mfy, cx, cy, NQ, 8, 0, 1, 0.15, 1.0, &nsplt, ksplt));
+    for (int j = 3; j < ND - 3; ++j) CHECK(fabs(qu[(size_t)j * ND + 5] - 3.25) < 1e-13, "damping leaves a uniform field alone");
+    free(d6u), free(d6v), free(qu);
+  }
 
   /* ---- remap with pe1 == pe2: identity to rounding, delp = diff(ak + bk ps) bit for bit */
   double ak[NPZ + 1], bk[NPZ + 1];

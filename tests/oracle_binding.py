@@ -183,3 +183,25 @@ def map_field_col(use_cs, pe1, pe2, q, iv, kord, q_min=0.0, qs=0.0):
     pe2 = np.ascontiguousarray(pe2, dtype=q.dtype)
     getattr(lib(), f"orc_{s}_map_field_col")(int(bool(use_cs)), int(km), _p(pe1), _p(pe2), _p(out), int(iv), int(kord), ct(q_min), ct(qs))
     return out
+
+
+def tracer_2d_damp(case, hord, nord_tr, trdm, del6_u, del6_v, da_min, q_split=0, lim_fac=1.0):
+    """tracer_2d with tracer damping (trdm2 > 1e-4: deln_flux on the first sub-step, tp_core.F90:1239-1387); del6_u
+    [6, n+7, n+6], del6_v [6, n+6, n+7] and da_min are the fv_grid_type members of fv_arrays.F90:124,183."""
+    s, ct = _sfx(case.dtype)
+    g = case.metrics()
+    out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    dst, src = halo_offsets(case.n)
+    nsplt = C.c_int(0)
+    ksplt = np.zeros(case.npz, dtype=np.int32)
+    cmax = np.zeros(case.npz, dtype=case.dtype)
+    d6u = np.ascontiguousarray(del6_u, dtype=case.dtype)
+    d6v = np.ascontiguousarray(del6_v, dtype=case.dtype)
+    getattr(lib(), f"orc_{s}_tracer_2d_damp")(
+        6, case.n, case.npz, case.nq, _p(out["q"]), _p(out["dp1"]), _p(out["mfx"]), _p(out["mfy"]), _p(out["cx"]),
+        _p(out["cy"]), _p(g["area"]), _p(g["rarea"]), _p(g["dx"]), _p(g["dy"]), _p(g["dxa"]), _p(g["dya"]), _p(g["sin_sg"]),
+        _p(dst), _p(src), C.c_int64(dst.size), int(hord), int(q_split), ct(lim_fac), C.byref(nsplt), _p(ksplt), _p(cmax),
+        _p(d6u), _p(d6v), ct(da_min), int(nord_tr), ct(trdm))
+    out["nsplt"] = nsplt.value
+    out["ksplt"] = ksplt
+    return out

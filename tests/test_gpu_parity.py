@@ -470,3 +470,33 @@ def test_map1_ppm_and_map_scalar_against_the_oracle(oracle, case_factory, kord, 
                 want = ob.map_field_col(use_cs, pe1, pe2, col, iv, kord, q_min=q_min, qs=float(qs[t, j + 2, i + 2]) if qs is not None else 0.0)
                 assert np.array_equal(got[t, :, j + 2, i + 2], want), (iv, t, i, j, np.abs(got[t, :, j + 2, i + 2] - want).max())
     ctx.close()
+
+
+# ---- tracer damping: deln_flux on the first sub-step -------------------------------------------------------------------------
+@pytest.mark.parametrize("nord", [0, 1, 2])
+@pytest.mark.parametrize("courant", [0.7, 1.8])
+def test_tracer_damping_deln_flux(oracle, case_factory, nord, courant, mode):
+    """tracer_2d with trdm2 > 1e-4 (fv_tracer2d.F90:487-494, 527-532 -> deln_flux, tp_core.F90:1239-1387): del-2 / del-4 / del-6,
+    with and without sub-cycling.  The library applies the damping fluxes as a correction of the advected field (same terms, other
+    summation order), so the bar is the north-star tolerance, not bit equality; the dp1 / cx / cy / mfx / mfy post-state and the
+    sub-step counts are unchanged by damping."""
+    import oracle_binding as ob
+    from fv3atm_b200 import cubed_sphere as cs
+    case = case_factory(24, 16, 9, "float64", courant=courant)
+    d6u, d6v, da_min = cs.damping_metrics(case.grid)
+    trdm = 0.15
+    ref = ob.tracer_2d_damp(case, 8, nord, trdm, d6u, d6v, da_min)
+    plain = oracle.tracer_2d(case, hord=8)
+    ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+    ctx.set_damping(d6u, d6v, da_min)
+    out = {k: np.array(getattr(case, k), copy=True, order="C") for k in ("q", "dp1", "mfx", "mfy", "cx", "cy")}
+    nsplt, ksplt = ctx.tracer_2d(out["q"], out["dp1"], out["mfx"], out["mfy"], out["cx"], out["cy"], 8, nord_tr=nord, trdm=trdm)
+    ctx.close()
+    assert nsplt == ref["nsplt"] and np.array_equal(ksplt, ref["ksplt"])
+    nd = norm_diff(out["q"], ref["q"])
+    assert nd.max() <= 1e-12, f"nord={nord}: {nd}"
+    assert norm_diff(ref["q"], plain["q"]).max() > 1e-4   # the damping does something in this case
+    sl = slice(NG, -NG)
+    assert np.array_equal(out["dp1"][..., sl, sl], plain["dp1"][..., sl, sl])
+    for k in ("cx", "cy", "mfx", "mfy"):
+        assert np.array_equal(out[k], plain[k]), k
