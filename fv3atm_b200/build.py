@@ -19,7 +19,7 @@ SOURCES = [("fv3t_api.cu", "fv3t_api.o", ["--fmad=false"]),
            ("fv3t_fast.cu", "fv3t_fast_f32.o", ["--fmad=true", "-DFV3T_INST_F32"]),
            ("fv3t_exact.cu", "fv3t_exact_f64.o", ["--fmad=false", "-DFV3T_INST_F64"]),
            ("fv3t_exact.cu", "fv3t_exact_f32.o", ["--fmad=false", "-DFV3T_INST_F32"])]
-HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_advect5.cuh", "fv3t_advect5_launch.cuh", "fv3t_deln.cuh", "fv3t_remap4.cuh", "fv3t_remap.cuh",
+HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_advect5.cuh", "fv3t_advect5_launch.cuh", "fv3t_deln.cuh", "fv3t_tp2d.cuh", "fv3t_remap4.cuh", "fv3t_remap.cuh",
            "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
 
 NVCC_FLAGS = [
@@ -49,12 +49,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     procs = []
     dev = ["-DFV3T_A5_DEV"] if os.environ.get("FV3T_A5_DEV") else []  # development builds: k_advect5 for hord 8 / 10 only
+    only = [x for x in os.environ.get("FV3T_BUILD_ONLY", "").split(",") if x]  # development: recompile the named objects only
+    reuse = []
     for src, objname, extra in SOURCES:
         obj = os.path.join(CSRC, objname)
+        if only and not any(o in objname for o in only) and os.path.exists(obj):
+            reuse.append(obj)
+            continue
         extra = extra + dev
         cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((obj, subprocess.Popen(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    objs = []
+    objs = list(reuse)
     for obj, pr in procs:
         out, _ = pr.communicate()
         if verbose or pr.returncode != 0:

@@ -21,6 +21,7 @@
 #include "fv3t_remap2.cuh"
 #include "fv3t_fast.h"
 #include "fv3t_deln.cuh"
+#include "fv3t_tp2d.cuh"
 
 namespace {
 
@@ -245,6 +246,8 @@ template <class T> struct Impl {
   int substep(int it, int hord, T lim_fac);
   int prepare(int hord, bool allow5 = true);
   int apply_damping(int it, bool mf_scaled);
+  int fv_tp_2d_host(int nlev, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx, const T* yfx, const T* ra_x,
+                    const T* ra_y, T lim_fac, const T* mfx, const T* mfy, const T* mass, int nord, T damp_c);
   int alloc5();
   int finish();
   int tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out);
@@ -819,6 +822,123 @@ template <class T> int Impl<T>::apply_damping(int it, bool mf_scaled) {
     kend(KC_ADVECT);
   }
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- fv_tp_2d as an operator (tp_core.F90:110-249; fv3t_tp2d.cuh): host arrays in, fluxes out -----------------------------
+template <class T> static cudaError_t tp2d_flux(int ord, const fv3t::Tp2dFlux<T>& p, dim3 grid, cudaStream_t st) {
+  switch (ord) {
+#define FV3T_TP2D_CASE(O) case O: fv3t::k_tp2d_flux<T, O><<<grid, 128, 0, st>>>(p); break;
+    FV3T_TP2D_CASE(1) FV3T_TP2D_CASE(2) FV3T_TP2D_CASE(3) FV3T_TP2D_CASE(4) FV3T_TP2D_CASE(5) FV3T_TP2D_CASE(-5) FV3T_TP2D_CASE(6)
+    FV3T_TP2D_CASE(7) FV3T_TP2D_CASE(8) FV3T_TP2D_CASE(9) FV3T_TP2D_CASE(10) FV3T_TP2D_CASE(11) FV3T_TP2D_CASE(12) FV3T_TP2D_CASE(13)
+#undef FV3T_TP2D_CASE
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+template <class T>
+int Impl<T>::fv_tp_2d_host(int nlev, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx, const T* yfx,
+                           const T* ra_x, const T* ra_y, T lim_fac, const T* mfx_h, const T* mfy_h, const T* mass_h, int nord,
+                           T damp_c) {
+  if (!((hord >= 1 && hord <= 13) || hord == -5)) return fail("fv3tracer: hord = %d is not a scheme of xppm/yppm", hord);
+  if (nlev < 1) return fail("fv3tracer: fv_tp_2d: nlev = %d", nlev);
+  if (!q || !crx || !cry || !fx || !fy || !xfx || !yfx || !ra_x || !ra_y) return fail("fv3tracer: fv_tp_2d: null array");
+  if ((mfx_h == nullptr) != (mfy_h == nullptr)) return fail("fv3tracer: fv_tp_2d: mfx and mfy must be given together (tp_core.F90:209)");
+  const bool tracer = mfx_h != nullptr;
+  // tp_core.F90:229-234 (tracer branch: nord, damp_c AND mass) / :243-248 (nord, damp_c)
+  const bool damp_on = nord >= 0 && damp_c > T(1.e-4) && (tracer ? mass_h != nullptr : true);
+  const bool with_mass = tracer && damp_on;
+  if (damp_on) {
+    if (!del6_u) return fail("fv3tracer: fv_tp_2d: damping needs the damping metrics (fv3t_*_set_damping)");
+    if (nord > 2) return fail("fv3tracer: fv_tp_2d: nord = %d outside 0..2 (deln_flux needs nord + 1 <= ng halo cells)", nord);
+  }
+  CK(cudaSetDevice(device));
+  const size_t nd = n + 6, P = (size_t)nt * nlev;
+  const size_t s_pl = P * nd * nd, s_xf = P * (n + 1) * nd, s_ra = P * n * nd, s_f = P * (n + 1) * n, s_dx = P * nd * (nd + 1);
+  // one allocation, carved: q, q_mid, crx, xfx, fx2, cry, yfx, fy2, ra_x, ra_y, fx, fy [, mfx, mfy] [, mass] [, dfx2, dfy2, d2]
+  size_t total = 2 * s_pl + 6 * s_xf + 2 * s_ra + 2 * s_f + (tracer ? 2 * s_f : 0) + (with_mass ? s_pl : 0) +
+                 (damp_on ? 2 * s_dx + s_pl : 0);
+  T* base = nullptr;
+  CK(cudaMalloc((void**)&base, total * sizeof(T)));
+  struct Free {
+    T* p;
+    ~Free() { cudaFree(p); }
+  } guard{base};
+  T* cur_p = base;
+  auto take = [&](size_t ne) { T* r = cur_p; cur_p += ne; return r; };
+  T *d_q = take(s_pl), *d_mid = take(s_pl), *d_crx = take(s_xf), *d_xfx = take(s_xf), *d_fx2 = take(s_xf), *d_cry = take(s_xf),
+    *d_yfx = take(s_xf), *d_fy2 = take(s_xf), *d_rax = take(s_ra), *d_ray = take(s_ra), *d_fx = take(s_f), *d_fy = take(s_f);
+  T *d_mfx = tracer ? take(s_f) : nullptr, *d_mfy = tracer ? take(s_f) : nullptr, *d_mass = with_mass ? take(s_pl) : nullptr;
+  T *d_dfx = damp_on ? take(s_dx) : nullptr, *d_dfy = damp_on ? take(s_dx) : nullptr, *d_d2 = damp_on ? take(s_pl) : nullptr;
+  auto up = [&](T* d, const T* h, size_t ne) { return cudaMemcpyAsync(d, h, ne * sizeof(T), cudaMemcpyHostToDevice, stream); };
+  CK(up(d_q, q, s_pl));
+  CK(up(d_crx, crx, s_xf));
+  CK(up(d_xfx, xfx, s_xf));
+  CK(up(d_cry, cry, s_xf));
+  CK(up(d_yfx, yfx, s_xf));
+  CK(up(d_rax, ra_x, s_ra));
+  CK(up(d_ray, ra_y, s_ra));
+  if (tracer) {
+    CK(up(d_mfx, mfx_h, s_f));
+    CK(up(d_mfy, mfy_h, s_f));
+  }
+  if (with_mass) CK(up(d_mass, mass_h, s_pl));
+
+  const int ord_in = hord == 10 ? 8 : hord, ord_ou = hord;  // tp_core.F90:157-162
+  const int nd_i = (int)nd;
+  dim3 grid(64, (unsigned)P);
+  const long pl_x = (long)(n + 1) * nd_i, pl_f = (long)(n + 1) * n;
+  fv3t::Tp2dFlux<T> f{};
+  f.n = n;
+  f.nlev = nlev;
+  f.lim_fac = lim_fac;
+  // fy2 = yppm(q, dir-2 view), i = isd..ied
+  f.src = d_q, f.cour = d_cry, f.flux = d_fy2, f.dxa = dya, f.c_plane = f.f_plane = pl_x, f.c_pitch = f.f_pitch = nd_i;
+  f.c_l0 = f.f_l0 = -2, f.dir = 1, f.view = 2, f.l_lo = -2, f.l_hi = n + 3;
+  CK(tp2d_flux<T>(ord_in, f, grid, stream));
+  fv3t::Tp2dMid<T> m{d_q, d_fy2, d_yfx, area, d_ray, d_mid, n, nlev, 1};
+  fv3t::k_tp2d_mid<T><<<grid, 256, 0, stream>>>(m);
+  // fx = xppm(q_i), j = 1..n
+  f.src = d_mid, f.cour = d_crx, f.flux = d_fx, f.dxa = dxa, f.c_plane = pl_x, f.f_plane = pl_f, f.c_pitch = f.f_pitch = n + 1;
+  f.c_l0 = -2, f.f_l0 = 1, f.dir = 0, f.view = 0, f.l_lo = 1, f.l_hi = n;
+  CK(tp2d_flux<T>(ord_ou, f, grid, stream));
+  // fx2 = xppm(q, dir-1 view), j = jsd..jed
+  f.src = d_q, f.flux = d_fx2, f.f_plane = pl_x, f.f_l0 = -2, f.view = 1, f.l_lo = -2, f.l_hi = n + 3;
+  CK(tp2d_flux<T>(ord_in, f, grid, stream));
+  m = fv3t::Tp2dMid<T>{d_q, d_fx2, d_xfx, area, d_rax, d_mid, n, nlev, 0};
+  fv3t::k_tp2d_mid<T><<<grid, 256, 0, stream>>>(m);
+  // fy = yppm(q_j), i = 1..n
+  f.src = d_mid, f.cour = d_cry, f.flux = d_fy, f.dxa = dya, f.c_plane = pl_x, f.f_plane = pl_f, f.c_pitch = nd_i, f.f_pitch = n;
+  f.c_l0 = -2, f.f_l0 = 1, f.dir = 1, f.view = 0, f.l_lo = 1, f.l_hi = n;
+  CK(tp2d_flux<T>(ord_ou, f, grid, stream));
+  fv3t::Tp2dAvg<T> av{d_fx, d_fy, d_fx2, d_fy2, tracer ? d_mfx : d_xfx, tracer ? d_mfy : d_yfx, n, tracer ? 1 : 0};
+  fv3t::k_tp2d_avg<T><<<grid, 256, 0, stream>>>(av);
+  if (damp_on) {
+    const T damp = (T)std::pow((double)(damp_c * da_min), (double)(nord + 1));
+    const T* operand = d_q;
+    if (!with_mass) {
+      fv3t::k_tp2d_scale<T><<<1184, 256, 0, stream>>>(d_d2, d_q, damp, (long)s_pl);
+      operand = d_d2;
+    }
+    fv3t::DelnParams<T> dp{operand, d_dfx, d_dfy, d_d2, del6_u, del6_v, rarea, n, nlev, nord, nord, 1, (long)(nlev * nd * nd)};
+    fv3t::k_deln_flux<T><<<grid, 256, 0, stream>>>(dp);
+    for (int s = 1; s <= nord; ++s) {
+      dp.nt = nord - s;
+      dp.first = 0;
+      dp.src = d_d2;
+      fv3t::k_deln_div<T><<<grid, 256, 0, stream>>>(dp);
+      fv3t::k_deln_flux<T><<<grid, 256, 0, stream>>>(dp);
+    }
+    fv3t::Tp2dDampAdd<T> da{d_fx, d_fy, d_dfx, d_dfy, with_mass ? d_mass : nullptr, damp, n};
+    fv3t::k_tp2d_damp_add<T><<<grid, 256, 0, stream>>>(da);
+  }
+  fv3t::k_tp2d_corners<T><<<(unsigned)P, 64, 0, stream>>>(d_q, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(fx, d_fx, s_f * sizeof(T), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(fy, d_fy, s_f * sizeof(T), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(q, d_q, s_pl * sizeof(T), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
   return 0;
 }
 
@@ -1415,6 +1535,12 @@ extern "C" int fv3t_device_count(void) {
                          nd * sizeof(REAL), (size_t)km * nq, cudaMemcpyDeviceToHost, I->stream));                              \
     CK(cudaStreamSynchronize(I->stream));                                                                                      \
     return 0;                                                                                                                  \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_fv_tp_2d(fv3t_ctx* ctx, int nlev, REAL* q, const REAL* crx, const REAL* cry, int hord, REAL* fx,   \
+                                     REAL* fy, const REAL* xfx, const REAL* yfx, const REAL* ra_x, const REAL* ra_y,           \
+                                     REAL lim_fac, const REAL* mfx, const REAL* mfy, const REAL* mass, int nord, REAL damp_c) { \
+    NEED(ctx, P);                                                                                                              \
+    return I->fv_tp_2d_host(nlev, q, crx, cry, hord, fx, fy, xfx, yfx, ra_x, ra_y, lim_fac, mfx, mfy, mass, nord, damp_c);      \
   }                                                                                                                            \
   extern "C" int fv3t_##P##_tracer_2d_begin(fv3t_ctx* ctx, int nq, int q_split, REAL* cmax_local) {                            \
     NEED(ctx, P);                                                                                                              \

@@ -176,13 +176,21 @@ template <class T> cudaError_t fast_remap4(Remap4Params<T> p, int akord, cudaStr
   return launch_remap4_lpl<T, 9>(p, stream);
 }
 
+template <class T> static bool remap3_offsets_fit(const Remap3Params<T>& p);
 template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaStream_t stream) {
+  if (!remap3_offsets_fit(p)) return cudaErrorInvalidValue;
   dim3 grid((p.n * p.n + 127) / 128, p.ntiles);
   k_remap_coef3<T><<<grid, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
+// the remap kernels index inside a column with 32-bit offsets
+template <class T> static bool remap3_offsets_fit(const Remap3Params<T>& p) {
+  return (long)(p.km + 1) * (p.n + 6) * (p.n + 6) < (1L << 31) && (long)(p.km + 1) * (p.n + 2) < (1L << 31);
+}
+
 template <class T, int AK> static cudaError_t launch_remap3(const Remap3Params<T>& p, cudaStream_t stream) {
+  if (!remap3_offsets_fit(p)) return cudaErrorInvalidValue;
   dim3 grid(p.nql < 0 ? p.nq - p.iq0 : p.nql, (p.n * p.n + 127) / 128, p.ntiles);
   static const int minb = getenv("FV3T_REMAP_MINB") ? atoi(getenv("FV3T_REMAP_MINB")) : 4;  // tuning knob: 4 -> 128 regs, 5 -> 96, 6 -> 80
   if (minb == 5)

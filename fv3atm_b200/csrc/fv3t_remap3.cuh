@@ -15,6 +15,8 @@
 // Results agree with the FMA-free oracle to ~1e-15 normalised on smooth data (the 1e-12 bar is asserted in the tests); the
 // strict kernel (fv3t_remap2.cuh, FV3T_STRICT=1) stays bit-identical.  Tracer sets with mixed kord use the strict kernel.
 #pragma once
+#include <type_traits>
+
 #include "fv3t_advect4.cuh"
 #include "fv3t_remap2.cuh"
 
@@ -47,7 +49,8 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
   T* RD1 = p.RD1 + (long)t * plane * km + col;
   T* R2 = p.R2 + (long)t * plane * km + col;
   T* delp = p.delp + (long)t * plane * km + col;
-  auto PE1 = [&](int k) -> T { return pe[(long)(k - 1) * pe_ld1]; };
+  const int ipl = (int)plane, ipe = (int)pe_ld1;  // 32-bit offsets inside a column (see remap3_column)
+  auto PE1 = [&](int k) -> T { return pe[(k - 1) * ipe]; };
   const T ps = PE1(km + 1);
   auto PE2 = [&](int k) -> T { return k == 1 ? p.ptop : (k == km + 1 ? ps : add_rn(p.ak[k - 1], mul_rn(p.bk[k - 1], ps))); };  // uncontracted: delp is caller-visible
   T pa = PE1(1), pb = PE1(2), pc = PE1(3);
@@ -63,9 +66,9 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
     d4 = dpm / dpc;
     bet = T(2) + d4 + d4 - gprev;
     gprev = d4 / bet;
-    P1[(long)(k - 1) * plane] = Pair<T>{d4, T(1) / bet};
-    GAM[(long)(k - 1) * plane] = gprev;
-    RD1[(long)(k - 1) * plane] = T(1) / dpc;
+    P1[(k - 1) * ipl] = Pair<T>{d4, T(1) / bet};
+    GAM[(k - 1) * ipl] = gprev;
+    RD1[(k - 1) * ipl] = T(1) / dpc;
     if (k < km) {
       pb = pc;
       pc = PE1(k + 2);
@@ -76,14 +79,14 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
   const T a_bot = T(1) + d4 * (d4 + T(1.5));
   const T cbot = T(2) * d4 * (d4 + T(1));
   const T den = d4 * (d4 + T(0.5)) - a_bot * gprev;
-  P1[(long)km * plane] = Pair<T>{cbot, a_bot};
-  GAM[(long)km * plane] = T(1) / den;
+  P1[km * ipl] = Pair<T>{cbot, a_bot};
+  GAM[km * ipl] = T(1) / den;
   T p2a = PE2(1);
   for (int k = 1; k <= km; ++k) {
     const T p2b = PE2(k + 1);
     const T dp2 = p2b - p2a;
-    delp[(long)(k - 1) * plane] = dp2;
-    R2[(long)(k - 1) * plane] = T(1) / dp2;
+    delp[(k - 1) * ipl] = dp2;
+    R2[(k - 1) * ipl] = T(1) / dp2;
     p2a = p2b;
   }
 }
@@ -98,14 +101,17 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   const T* pe = p.pe + (long)t * pe_ld2 * (n + 2) + (long)i + (long)j * pe_ld2;  // pe1(k) = pe[(k-1)*pe_ld1]
   const long col = (long)(j + 2) * nd + (i + 2);
   const long off = (((long)t * p.nq + iq) * km) * plane + col;
+  // offsets inside a column fit 32 bits ((km + 1) * plane < 2^31, checked by the launcher): one IMAD.WIDE per access instead of
+  // a 64 x 64-bit multiply
+  const int ipl = (int)plane, ipe = (int)pe_ld1;
   const T* __restrict__ qs = p.qsrc + off;
   T* __restrict__ qd = p.qdst + off;
   const Pair<T>* P1 = p.P1 + (long)t * plane * (km + 1) + col;
   const T* GAM = p.GAM + (long)t * plane * (km + 1) + col;
   const T* RD1 = p.RD1 + (long)t * plane * km + col;
   const T* R2 = p.R2 + (long)t * plane * km + col;
-  auto A1 = [&](int k) -> T { return qs[(long)(k - 1) * plane]; };
-  auto PE1 = [&](int k) -> T { return pe[(long)(k - 1) * pe_ld1]; };
+  auto A1 = [&](int k) -> T { return qs[(k - 1) * ipl]; };
+  auto PE1 = [&](int k) -> T { return pe[(k - 1) * ipe]; };
   const T ps = PE1(km + 1);
   auto PE2 = [&](int k) -> T { return k == 1 ? p.ptop : (k == km + 1 ? ps : add_rn(akp[k - 1], mul_rn(bkp[k - 1], ps))); };  // uncontracted: delp is caller-visible
 
@@ -115,35 +121,40 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   //      ahead of the dependent recurrence: the column walks through HBM with a plane-sized stride, and nothing but
   //      memory-level parallelism hides that latency (profiles/r01_remap3_v0_ncu.txt: 8 of 12 stall cycles per issue)
   constexpr int CH = 8;
+  // chunks whose levels are all interior run without the per-level bound tests (`full`), the first / last ones with them
   {
     T a1mm = A1(1), a1m = A1(2);
     const Pair<T> c1 = P1[0];
     T qk = (c1.a * a1mm + a1m) * c1.b;
     qv[1] = qk;
-    for (int k0 = 2; k0 <= km; k0 += CH) {
+    auto chunk = [&](auto full, int k0) {
+      constexpr bool FULL = decltype(full)::value;
       T an[CH];
       Pair<T> ck[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int k = k0 + u;
-        ck[u] = (k <= km) ? P1[(long)(k - 1) * plane] : Pair<T>{T(0), T(0)};
-        an[u] = (k + 1 <= km) ? A1(k + 1) : T(0);
+        ck[u] = (FULL || k <= km) ? P1[(k - 1) * ipl] : Pair<T>{T(0), T(0)};
+        an[u] = (FULL || k + 1 <= km) ? A1(k + 1) : T(0);
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int k = k0 + u;
-        if (k <= km) {
+        if (FULL || k <= km) {
           qk = (T(3) * (a1mm + ck[u].a * a1m) - qk) * ck[u].b;
           qv[k] = qk;
-          if (k < km) {
+          if (FULL || k < km) {
             a1mm = a1m;
             a1m = an[u];
           }
         }
       }
-    }
-    const Pair<T> cb = P1[(long)km * plane];
-    const T rden = GAM[(long)km * plane];
+    };
+    int k0 = 2;
+    for (; k0 + CH <= km; k0 += CH) chunk(std::true_type{}, k0);
+    for (; k0 <= km; k0 += CH) chunk(std::false_type{}, k0);
+    const Pair<T> cb = P1[km * ipl];
+    const T rden = GAM[km * ipl];
     qv[km + 1] = (cb.a * a1m + a1mm - cb.b * qk) * rden;
   }
 
@@ -151,26 +162,27 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   {
     T r = qv[km + 1];
     T ap = T(0), a0 = A1(km), am = A1(km - 1), amm = A1(km - 2);
-    for (int k0 = km; k0 >= 1; k0 -= CH) {
+    auto chunk = [&](auto full, int k0) {  // full: 4 <= k < km for every level of the chunk
+      constexpr bool FULL = decltype(full)::value;
       T qq[CH], gg[CH], an[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int k = k0 - u;
-        qq[u] = k >= 1 ? qv[k] : T(0);
-        gg[u] = k >= 1 ? GAM[(long)(k - 1) * plane] : T(0);
-        an[u] = (AK <= 16 && k - 3 >= 1) ? A1(k - 3) : T(0);
+        qq[u] = (FULL || k >= 1) ? qv[k] : T(0);
+        gg[u] = (FULL || k >= 1) ? GAM[(k - 1) * ipl] : T(0);
+        an[u] = (AK <= 16 && (FULL || k - 3 >= 1)) ? A1(k - 3) : T(0);
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int k = k0 - u;
-        if (k >= 1) {
+        if (FULL || k >= 1) {
           r = qq[u] - gg[u] * r;
           T c = r;
           if (AK <= 16) {
-            if (k == km || k == 2) {
+            if (!FULL && (k == km || k == 2)) {
               c = f_min(c, f_max(am, a0));
               c = f_max(c, f_min(am, a0));
-            } else if (k >= 3) {
+            } else if (FULL || k >= 3) {
               const T gm = am - amm;  // gam(k-1) = a1(k-1) - a1(k-2)
               const T gp = ap - a0;   // gam(k+1) = a1(k+1) - a1(k)
               if (gm * gp > T(0)) {
@@ -191,7 +203,12 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
           qv[k] = c;
         }
       }
-    }
+    };
+    int k0 = km;
+    chunk(std::false_type{}, k0);  // holds k = km
+    k0 -= CH;
+    for (; k0 - CH + 1 >= 4; k0 -= CH) chunk(std::true_type{}, k0);
+    for (; k0 >= 1; k0 -= CH) chunk(std::false_type{}, k0);
   }
 
   // ---- pass 3: source-layer-major sweep (see fv3t_remap2.cuh)
@@ -210,7 +227,7 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   // still cost 14 % because the compiler copies the freshly loaded register at the loop join and that copy waits at once.
   auto r2_request = [&](int kk) {  // target layer kk (1-based), clamped
     const int kc = kk <= km ? kk : km;
-    async_copy<sizeof(T)>(ring + (kk & 3) * rstride, R2 + (long)(kc - 1) * plane);
+    async_copy<sizeof(T)>(ring + (kk & 3) * rstride, R2 + (kc - 1) * ipl);
     async_commit();
   };
   r2_request(1);
@@ -221,7 +238,7 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   bool started = false;
 
   auto finalize = [&](int kk, T x, T dpkk) {
-    qd[(long)(kk - 1) * plane] = x;
+    qd[(kk - 1) * ipl] = x;
     if (kk >= 2) {
       const T m = x * dpkk;
       sum0 = sum0 + m;
@@ -231,7 +248,7 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   // value v of target layer k -> fillz pipeline (fv_fill.F90:86-128) or straight to memory
   auto emit = [&](T v) {
     if (!p.fill) {
-      qd[(long)(k - 1) * plane] = v;
+      qd[(k - 1) * ipl] = v;
     } else if (k == 1) {
       xa = v;
     } else if (k == 2) {
@@ -293,7 +310,7 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
     T n_pe = T(0), n_rd = T(0), n_a = T(0), n_c = T(0);
     if (l < km) {
       n_pe = PE1(l + 2);
-      n_rd = RD1[(long)l * plane];
+      n_rd = RD1[l * ipl];
       n_a = (l + 3 <= km) ? A1(l + 3) : T(0);
       n_c = (l + 3 <= km + 1) ? qv[l + 3] : T(0);
     }
@@ -392,8 +409,8 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
     const T fac = sum0 / sum1;
     for (int kk = 2; kk <= km; ++kk) {
       const T dp = PE2(kk + 1) - PE2(kk);
-      const T x = qd[(long)(kk - 1) * plane];
-      qd[(long)(kk - 1) * plane] = f_max(T(0), fac * (x * dp) / dp);
+      const T x = qd[(kk - 1) * ipl];
+      qd[(kk - 1) * ipl] = f_max(T(0), fac * (x * dp) / dp);
     }
   }
 }

@@ -13,7 +13,7 @@ FIELD = {"q": 0, "dp1": 1, "mfx": 2, "mfy": 3, "cx": 4, "cy": 5, "pe": 6, "delp"
 KCLASS = {"advect": 0, "remap": 1, "halo": 2, "cmax": 3, "scale": 4}
 
 # every symbol include/fv3tracer.h declares
-_PER_PREC = ["create", "tracer_2d", "tracer_2d_1L", "set_damping", "remap_tracers", "tracer_step", "mapn_tracer", "map_scalar", "map1_ppm", "map_field", "upload", "download", "set_vertical",
+_PER_PREC = ["create", "tracer_2d", "tracer_2d_1L", "set_damping", "remap_tracers", "tracer_step", "mapn_tracer", "map_scalar", "map1_ppm", "map_field", "fv_tp_2d", "upload", "download", "set_vertical",
              "tracer_2d_resident", "remap_tracers_resident", "remap_prepare", "tracer_2d_begin", "tracer_2d_set_cmax", "halo_local",
              "halo_pack", "halo_unpack", "halo_pack_host", "halo_unpack_host", "tracer_2d_substep", "tracer_2d_finish"]
 _COMMON = ["fv3t_last_error", "fv3t_device_count", "fv3t_destroy", "fv3t_sync", "fv3t_device_ptr", "fv3t_halo_strip_elems",

@@ -125,6 +125,23 @@ class TracerContext:
             qsp = L.ptr(qs)
         L.check(self._f("map_field")(self._h, L.ptr(q), qsp, int(iv), int(kord), self._ct(q_min), int(bool(use_cs))))
 
+    def fv_tp_2d(self, q, crx, cry, hord, xfx, yfx, ra_x, ra_y, lim_fac=1.0, mfx=None, mfy=None, mass=None, nord=-1,
+                 damp_c=0.0):
+        """fv_tp_2d (tp_core.F90:110-249) for nlev stacked 2-D fields per resident tile: q [nt, nlev, n+6, n+6] (in place: the
+        corner halos come back with the dir = 1 corner view), crx/xfx [nt, nlev, n+6, n+1], cry/yfx [nt, nlev, n+1, n+6],
+        ra_x [nt, nlev, n+6, n], ra_y [nt, nlev, n, n+6]; mfx [nt, nlev, n, n+1] and mfy [nt, nlev, n+1, n] both or neither;
+        mass like q or None; nord < 0 = absent.  Returns (fx [nt, nlev, n, n+1], fy [nt, nlev, n+1, n])."""
+        assert q.dtype == self.dtype and q.flags["C_CONTIGUOUS"] and q.ndim == 4
+        nt, nlev, n = q.shape[0], q.shape[1], self.n
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=self.dtype)
+        arrs = [c(a) for a in (crx, cry, xfx, yfx, ra_x, ra_y, mfx, mfy, mass)]
+        pp = [None if a is None else L.ptr(a) for a in arrs]
+        fx = np.zeros((nt, nlev, n, n + 1), dtype=self.dtype)
+        fy = np.zeros((nt, nlev, n + 1, n), dtype=self.dtype)
+        L.check(self._f("fv_tp_2d")(self._h, int(nlev), L.ptr(q), pp[0], pp[1], int(hord), L.ptr(fx), L.ptr(fy), pp[2], pp[3],
+                                     pp[4], pp[5], self._ct(lim_fac), pp[6], pp[7], pp[8], int(nord), self._ct(damp_c)))
+        return fx, fy
+
     # ---- device-resident operation -------------------------------------------------------------------
     def upload(self, field: str, host: np.ndarray, nq: int | None = None):
         host = np.ascontiguousarray(host, dtype=self.dtype)

@@ -129,6 +129,21 @@ int fv3t_device_count(void);
   int fv3t_##P##_map1_ppm(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord);                                     \
   int fv3t_##P##_map_field(fv3t_ctx* ctx, REAL* q, const REAL* qs, int iv, int kord, REAL q_min, int use_cs);            \
                                                                                                                         \
+  /* fv_tp_2d(q, crx, cry, npx, npy, hord, fx, fy, xfx, yfx, gridstruct, bd, ra_x, ra_y, lim_fac, mfx, mfy, mass, nord, damp_c)     \
+     ACS/model/tp_core.F90:110-133 -- the 2-D transport operator as the dynamical core calls it directly (d_sw.F90 for delp, pt, w, \
+     vorticity; fv_tracer2d.F90:510-531 for tracers), for `nlev` stacked 2-D fields per resident tile (tile-major, level fastest    \
+     within a tile).  Shapes per field as in the reference for a rank that owns a whole tile: q (isd:ied, jsd:jed) INOUT -- its     \
+     corner halos come back holding the dir = 1 copy_corners view, as in the reference (:189); crx, xfx (is:ie+1, jsd:jed);         \
+     cry, yfx (isd:ied, js:je+1); ra_x (is:ie, jsd:jed); ra_y (isd:ied, js:je); fx (is:ie+1, js:je) and fy (is:ie, js:je+1) OUT.    \
+     The Fortran optionals: mfx (is:ie+1, js:je) and mfy (is:ie, js:je+1) both given -> fluxes scaled by the mass fluxes (:209-220),\
+     both NULL -> by xfx, yfx (:236-242); mass (isd:ied, jsd:jed) or NULL; nord < 0 = absent.  deln_flux (:1239-1387) is added when \
+     damp_c > 1e-4 and nord is present (tracer branch: and mass is present), mass weighted in the tracer branch only; it needs      \
+     fv3t_*_set_damping's metrics and nord <= 2.  The grid terms (area, dxa, dya, rarea, del6_u, del6_v, da_min) are the            \
+     context's.  The reference's own operation order, bit for bit, for every hord. */                                              \
+  int fv3t_##P##_fv_tp_2d(fv3t_ctx* ctx, int nlev, REAL* q, const REAL* crx, const REAL* cry, int hord, REAL* fx, REAL* fy,       \
+                          const REAL* xfx, const REAL* yfx, const REAL* ra_x, const REAL* ra_y, REAL lim_fac, const REAL* mfx,     \
+                          const REAL* mfy, const REAL* mass, int nord, REAL damp_c);                                              \
+                                                                                                                        \
   /* tracer_2d immediately followed by the tracer remap (they are consecutive in ACS/model/fv_dynamics.F90:686-760), host    \
      arrays in and out, as ONE call: same arguments, same post-state as fv3t_*_tracer_2d + fv3t_*_remap_tracers (q, delp;     \
      dp1, cx, cy, mfx, mfy when nsplt /= 1).  Tracers are independent on this path, so they are pipelined one by one:         \

@@ -542,11 +542,9 @@ template <class T> struct Tp2dScratch {
   }
 };
 
-// fv_tp_2d (tp_core.F90:110-249).  mfx/mfy present -> tracer branch; nullptr -> xfx/yfx branch.
-// (deln_flux, the optional tracer damping, is not restated: trdm2 = 0 in every configuration in scope.)
-// deln_flux (tp_core.F90:1239-1387), the form with `mass` present and USE_SG undefined (CMake default): del-(2 nord + 2) damping
-// fluxes of the cell means, mass weighted, added to fx, fy.  q is ghosted on input and carries the dir = 1 corner view that
-// fv_tp_2d left in it (tp_core.F90:189).
+// deln_flux (tp_core.F90:1239-1387), both forms (`mass` present / absent), USE_SG undefined (CMake default): del-(2 nord + 2) damping
+// fluxes of the cell means (mass weighted when `mass` is given), added to fx, fy.  q is ghosted on input and carries the dir = 1
+// corner view that fv_tp_2d left in it (tp_core.F90:189).
 template <class T>
 static void deln_flux(int nord, int npx, int npy, T damp, V2<const T> q, V2<T> fx, V2<T> fy, const GridT<T>& g, const Bounds& bd,
                       const T* mass_p) {
@@ -557,8 +555,13 @@ static void deln_flux(int nord, int npx, int npy, T damp, V2<const T> q, V2<T> f
   V2<const T> del6_v{g.del6_v, isd, jsd, nxd + 1}, del6_u{g.del6_u, isd, jsd, nxd}, rarea{g.rarea, isd, jsd, nxd};
   V2<const T> mass{mass_p, isd, jsd, nxd};
   const int i1 = is - 1 - nord, i2 = ie + 1 + nord, j1 = js - 1 - nord, j2 = je + 1 + nord;
-  for (int j = j1; j <= j2; ++j)
-    for (int i = i1; i <= i2; ++i) d2(i, j) = q(i, j);  // `mass` present: damp is applied with the mass weighting below
+  if (!mass_p) {  // tp_core.F90:1275-1281
+    for (int j = j1; j <= j2; ++j)
+      for (int i = i1; i <= i2; ++i) d2(i, j) = damp * q(i, j);
+  } else {  // `mass` present: damp is applied with the mass weighting below
+    for (int j = j1; j <= j2; ++j)
+      for (int i = i1; i <= i2; ++i) d2(i, j) = q(i, j);
+  }
   if (nord > 0) copy_corners(d2, npx, npy, 1, bd, g);
   for (int j = js - nord; j <= je + nord; ++j)
     for (int i = is - nord; i <= ie + nord + 1; ++i) fx2(i, j) = del6_v(i, j) * (d2(i - 1, j) - d2(i, j));
@@ -577,6 +580,13 @@ static void deln_flux(int nord, int npx, int npy, T damp, V2<const T> q, V2<T> f
     for (int j = js - nt; j <= je + nt + 1; ++j)
       for (int i = is - nt; i <= ie + nt; ++i) fy2(i, j) = del6_u(i, j) * (d2(i, j) - d2(i, j - 1));
   }
+  if (!mass_p) {  // tp_core.F90:1372-1383
+    for (int j = js; j <= je; ++j)
+      for (int i = is; i <= ie + 1; ++i) fx(i, j) = fx(i, j) + fx2(i, j);
+    for (int j = js; j <= je + 1; ++j)
+      for (int i = is; i <= ie; ++i) fy(i, j) = fy(i, j) + fy2(i, j);
+    return;
+  }
   const T damp2 = T(0.5) * damp;
   for (int j = js; j <= je; ++j)
     for (int i = is; i <= ie + 1; ++i) fx(i, j) = fx(i, j) + damp2 * (mass(i - 1, j) + mass(i, j)) * fx2(i, j);
@@ -584,6 +594,8 @@ static void deln_flux(int nord, int npx, int npy, T damp, V2<const T> q, V2<T> f
     for (int i = is; i <= ie; ++i) fy(i, j) = fy(i, j) + damp2 * (mass(i, j - 1) + mass(i, j)) * fy2(i, j);
 }
 
+// fv_tp_2d (tp_core.F90:110-249).  mfx/mfy present -> tracer branch; nullptr -> xfx/yfx branch (delp, vorticity).
+// The Fortran optionals: mass_p == nullptr / nord < 0 / damp_c <= 1e-4 stand for "absent".
 template <class T>
 static void fv_tp_2d(V2<T> q, V2<const T> crx, V2<const T> cry, int npx, int npy, int hord, V2<T> fx, V2<T> fy,
                      V2<const T> xfx, V2<const T> yfx, const GridT<T>& g, const Bounds& bd, V2<const T> ra_x,
@@ -638,6 +650,10 @@ static void fv_tp_2d(V2<T> q, V2<const T> crx, V2<const T> cry, int npx, int npy
       for (int i = is; i <= ie + 1; ++i) fx(i, j) = T(0.5) * (fx(i, j) + fx2(i, j)) * xfx(i, j);
     for (int j = js; j <= je + 1; ++j)
       for (int i = is; i <= ie; ++i) fy(i, j) = T(0.5) * (fy(i, j) + fy2(i, j)) * yfx(i, j);
+    if (nord >= 0 && damp_c > T(1.e-4)) {  // tp_core.F90:243-248: delp / vorticity, no mass weighting
+      const T damp = std::pow(damp_c * g.da_min, (T)(nord + 1));
+      deln_flux<T>(nord, npx, npy, damp, cv(q), fx, fy, g, bd, nullptr);
+    }
   }
 }
 

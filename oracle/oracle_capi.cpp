@@ -79,6 +79,29 @@ void c_fv_tp_2d(int n, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy,
               lim_fac, mfx, mfy, w);
 }
 
+// fv_tp_2d with every optional argument: mfx/mfy (both or neither), mass, nord (< 0: absent), damp_c
+template <class T>
+void c_fv_tp_2d_full(int n, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx, const T* yfx, const T* ra_x,
+                     const T* ra_y, const T* area, const T* dxa, const T* dya, const T* rarea, const T* del6_u, const T* del6_v,
+                     T da_min, T lim_fac, const T* mfx, const T* mfy, const T* mass, int nord, T damp_c) {
+  const Bounds bd = Bounds::tile(n);
+  const long nxd = n + 6;
+  GridT<T> g{};
+  g.area = area;
+  g.rarea = rarea;
+  g.dxa = dxa;
+  g.dya = dya;
+  g.del6_u = del6_u;
+  g.del6_v = del6_v;
+  g.da_min = da_min;
+  Tp2dScratch<T> w;
+  w.size(bd);
+  fv_tp_2d<T>(V2<T>{q, bd.isd, bd.jsd, nxd}, V2<const T>{crx, 1, bd.jsd, (long)n + 1}, V2<const T>{cry, bd.isd, 1, nxd}, n + 1,
+              n + 1, hord, V2<T>{fx, 1, 1, (long)n + 1}, V2<T>{fy, 1, 1, (long)n}, V2<const T>{xfx, 1, bd.jsd, (long)n + 1},
+              V2<const T>{yfx, bd.isd, 1, nxd}, g, bd, V2<const T>{ra_x, 1, bd.jsd, (long)n}, V2<const T>{ra_y, bd.isd, 1, nxd},
+              lim_fac, mfx, mfy, w, mass, nord, damp_c);
+}
+
 template <class T> void c_copy_corners(T* q, int n, int dir) {
   const Bounds bd = Bounds::tile(n);
   GridT<T> g{};
@@ -206,6 +229,13 @@ template <class T> void c_map_field_col(int use_cs, int km, const T* pe1, const 
                                        const T* yfx, const T* ra_x, const T* ra_y, const T* area, const T* dxa, const T* dya, \
                                        T lim_fac, const T* mfx, const T* mfy) {                                                \
     c_fv_tp_2d<T>(n, q, crx, cry, hord, fx, fy, xfx, yfx, ra_x, ra_y, area, dxa, dya, lim_fac, mfx, mfy);                      \
+  }                                                                                                                            \
+  extern "C" void orc_##S##_fv_tp_2d_full(int n, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx,    \
+                                            const T* yfx, const T* ra_x, const T* ra_y, const T* area, const T* dxa,           \
+                                            const T* dya, const T* rarea, const T* del6_u, const T* del6_v, T da_min,          \
+                                            T lim_fac, const T* mfx, const T* mfy, const T* mass, int nord, T damp_c) {        \
+    c_fv_tp_2d_full<T>(n, q, crx, cry, hord, fx, fy, xfx, yfx, ra_x, ra_y, area, dxa, dya, rarea, del6_u, del6_v, da_min,      \
+                       lim_fac, mfx, mfy, mass, nord, damp_c);                                                                 \
   }                                                                                                                            \
   extern "C" void orc_##S##_copy_corners(T* q, int n, int dir) { c_copy_corners<T>(q, n, dir); }                             \
   extern "C" void orc_##S##_remap_tracers(int ntiles, int n, int km, int nq, const T* pe, const T* ak, const T* bk, T ptop, \

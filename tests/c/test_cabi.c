@@ -102,6 +102,25 @@ int main(void) {
     free(d6u), free(d6v), free(qu);
   }
 
+  /* ---- fv_tp_2d as an operator: a uniform field at rest has the flux  field value x flux area  on every face, with and without
+     mass fluxes; the two are given together or not at all */
+  {
+    const int nlev = 2;
+    const size_t npl = 6 * (size_t)nlev;
+    double* qf = filled(npl * plane, 3.25);
+    double *crx = filled(npl * ND * (N + 1), 0.0), *cry = filled(npl * ND * (N + 1), 0.0);
+    double *xfx = filled(npl * ND * (N + 1), 2.0), *yfx = filled(npl * ND * (N + 1), 2.0);
+    double *rax = filled(npl * ND * N, 1.0), *ray = filled(npl * ND * N, 1.0);
+    double *fx = filled(npl * N * (N + 1), -1.0), *fy = filled(npl * N * (N + 1), -1.0), *mf = filled(npl * N * (N + 1), 4.0);
+    OK(fv3t_f64_fv_tp_2d(ctx, nlev, qf, crx, cry, 10, fx, fy, xfx, yfx, rax, ray, 1.0, NULL, NULL, NULL, -1, 0.0));
+    for (size_t e = 0; e < npl * N * (N + 1); ++e) CHECK(fx[e] == 6.5 && fy[e] == 6.5, "fv_tp_2d: flux of a uniform field at rest = q * xfx");
+    OK(fv3t_f64_fv_tp_2d(ctx, nlev, qf, crx, cry, 8, fx, fy, xfx, yfx, rax, ray, 1.0, mf, mf, NULL, -1, 0.0));
+    for (size_t e = 0; e < npl * N * (N + 1); ++e) CHECK(fx[e] == 13.0 && fy[e] == 13.0, "fv_tp_2d: ... = q * mfx with mass fluxes");
+    CHECK(fv3t_f64_fv_tp_2d(ctx, nlev, qf, crx, cry, 5, fx, fy, xfx, yfx, rax, ray, 1.0, mf, NULL, NULL, -1, 0.0) != 0, "mfx without mfy is an error");
+    CHECK(fv3t_f64_fv_tp_2d(ctx, nlev, qf, crx, cry, 14, fx, fy, xfx, yfx, rax, ray, 1.0, NULL, NULL, NULL, -1, 0.0) != 0, "hord 14 is not a scheme");
+    free(qf), free(crx), free(cry), free(xfx), free(yfx), free(rax), free(ray), free(fx), free(fy), free(mf);
+  }
+
   /* ---- remap with pe1 == pe2: identity to rounding, delp = diff(ak + bk ps) bit for bit */
   double ak[NPZ + 1], bk[NPZ + 1];
   const double ptop = 100.0, ps = 1.0e5;

@@ -205,3 +205,23 @@ def tracer_2d_damp(case, hord, nord_tr, trdm, del6_u, del6_v, da_min, q_split=0,
     out["nsplt"] = nsplt.value
     out["ksplt"] = ksplt
     return out
+
+
+def fv_tp_2d(q, crx, cry, hord, xfx, yfx, ra_x, ra_y, area, dxa, dya, rarea=None, del6_u=None, del6_v=None, da_min=0.0,
+             lim_fac=1.0, mfx=None, mfy=None, mass=None, nord=-1, damp_c=0.0):
+    """fv_tp_2d (tp_core.F90:110-249) for ONE tile and one 2-D field: q [n+6, n+6] (ghosted; returned with the corner view the
+    reference leaves in it), crx/xfx [n+6, n+1], cry/yfx [n+1, n+6], ra_x [n+6, n], ra_y [n, n+6]; mfx [n, n+1] / mfy [n+1, n] both
+    or neither; mass [n+6, n+6] or None; nord < 0 = absent.  Returns (fx [n, n+1], fy [n+1, n], q)."""
+    s, ct = _sfx(q.dtype)
+    dt = q.dtype
+    n = q.shape[0] - 6
+    qq = np.array(q, copy=True, order="C")
+    fx = np.zeros((n, n + 1), dtype=dt)
+    fy = np.zeros((n + 1, n), dtype=dt)
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    keep = [c(a) for a in (crx, cry, xfx, yfx, ra_x, ra_y, area, dxa, dya, rarea, del6_u, del6_v, mfx, mfy, mass)]
+    pp = [None if a is None else _p(a) for a in keep]
+    getattr(lib(), f"orc_{s}_fv_tp_2d_full")(
+        n, _p(qq), pp[0], pp[1], int(hord), _p(fx), _p(fy), pp[2], pp[3], pp[4], pp[5], pp[6], pp[7], pp[8], pp[9], pp[10],
+        pp[11], ct(da_min), ct(lim_fac), pp[12], pp[13], pp[14], int(nord), ct(damp_c))
+    return fx, fy, qq
