@@ -20,7 +20,7 @@ SOURCES = [("fv3t_api.cu", "fv3t_api.o", ["--fmad=false"]),
            ("fv3t_exact.cu", "fv3t_exact_f64.o", ["--fmad=false", "-DFV3T_INST_F64"]),
            ("fv3t_exact.cu", "fv3t_exact_f32.o", ["--fmad=false", "-DFV3T_INST_F32"])]
 HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_advect5.cuh", "fv3t_advect5_launch.cuh", "fv3t_deln.cuh", "fv3t_tp2d.cuh", "fv3t_remap4.cuh", "fv3t_remap.cuh",
-           "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
+           "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_remap5.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

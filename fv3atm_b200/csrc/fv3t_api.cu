@@ -1124,7 +1124,7 @@ template <class T> int Impl<T>::remap_alloc() {
   CK(dalloc((void**)&P1, e1 * sizeof(fv3t::Pair<T>)));
   CK(dalloc((void**)&GAM, e1 * sizeof(T)));
   CK(dalloc((void**)&RD1, sz_c() * nt * sizeof(T)));
-  CK(dalloc((void**)&R2, sz_c() * nt * sizeof(T)));
+  CK(dalloc((void**)&R2, 2 * sz_c() * nt * sizeof(T)));  // Pair{1/dp2, pe2(k+1)} for k_remap5, 1/dp2 for k_remap3
   return 0;
 }
 

@@ -177,10 +177,20 @@ template <class T> cudaError_t fast_remap4(Remap4Params<T> p, int akord, cudaStr
 }
 
 template <class T> static bool remap3_offsets_fit(const Remap3Params<T>& p);
+// FV3T_REMAP5=1 selects the two-walk kernel pair of fv3t_remap5.cuh (parity-green, but SLOWER on B200: 84.9 ms against 76.6 ms at
+// C768 L127 x9 fp64 -- see the header); the default is the three-walk pair k_remap_coef3 / k_remap3.  Both launchers consult the
+// same flag: the coefficient arrays mean different things to the two pairs.
+static bool remap_two_walk() {
+  static const bool v = getenv("FV3T_REMAP5") && atoi(getenv("FV3T_REMAP5")) != 0;
+  return v;
+}
 template <class T> cudaError_t fast_remap_coef3(const Remap3Params<T>& p, cudaStream_t stream) {
   if (!remap3_offsets_fit(p)) return cudaErrorInvalidValue;
   dim3 grid((p.n * p.n + 127) / 128, p.ntiles);
-  k_remap_coef3<T><<<grid, 128, 0, stream>>>(p);
+  if (remap_two_walk() && p.km >= 4)
+    k_remap_coef5<T><<<grid, 128, 0, stream>>>(p);
+  else
+    k_remap_coef3<T><<<grid, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -192,7 +202,15 @@ template <class T> static bool remap3_offsets_fit(const Remap3Params<T>& p) {
 template <class T, int AK> static cudaError_t launch_remap3(const Remap3Params<T>& p, cudaStream_t stream) {
   if (!remap3_offsets_fit(p)) return cudaErrorInvalidValue;
   dim3 grid(p.nql < 0 ? p.nq - p.iq0 : p.nql, (p.n * p.n + 127) / 128, p.ntiles);
-  static const int minb = getenv("FV3T_REMAP_MINB") ? atoi(getenv("FV3T_REMAP_MINB")) : 4;  // tuning knob: 4 -> 128 regs, 5 -> 96, 6 -> 80
+  // CTAs per SM: fp64 4 (128 registers, no spills; 5 spills and is slower), fp32 6 (80 registers); FV3T_REMAP_MINB overrides
+  static const int minb = getenv("FV3T_REMAP_MINB") ? atoi(getenv("FV3T_REMAP_MINB")) : (sizeof(T) == 4 ? 6 : 4);
+  if (remap_two_walk() && p.km >= 4) {
+    if (minb == 5)
+      k_remap5<T, AK, 128, 5><<<grid, 128, 0, stream>>>(p);
+    else
+      k_remap5<T, AK, 128, 4><<<grid, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   if (minb == 5)
     k_remap3<T, AK, true, 128, 5><<<grid, 128, 0, stream>>>(p);
   else if (minb == 6)

@@ -8,6 +8,7 @@
 #include "fv3t_advect4.cuh"
 #include "fv3t_advect5.cuh"
 #include "fv3t_remap3.cuh"
+#include "fv3t_remap5.cuh"
 #include "fv3t_remap4.cuh"
 
 namespace fv3t {

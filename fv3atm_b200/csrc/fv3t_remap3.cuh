@@ -31,7 +31,7 @@ template <class T> struct Remap3Params {
   Pair<T>* P1;     // (isd:ied, jsd:jed, km+1): {d4, 1/bet}; level 1 {ctop, 1/bet1}; level km+1 {cbot, a_bot}
   T* GAM;          // (isd:ied, jsd:jed, km+1): gam;   level km+1: 1/den
   T* RD1;          // (isd:ied, jsd:jed, km):   1/dp1
-  T* R2;           // (isd:ied, jsd:jed, km): 1/dp2
+  T* R2;           // storage of 2 x (isd:ied, jsd:jed, km), read as Pair: {1/dp2(k), pe2(k+1)}
   T ptop;
   int n, km, nq, ntiles, fill;
   int iq0 = 0, nql = -1;  // this launch remaps tracers iq0 .. iq0+nql-1 of the nq resident ones (nql < 0: all)
@@ -47,7 +47,7 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
   Pair<T>* P1 = p.P1 + (long)t * plane * (km + 1) + col;
   T* GAM = p.GAM + (long)t * plane * (km + 1) + col;
   T* RD1 = p.RD1 + (long)t * plane * km + col;
-  T* R2 = p.R2 + (long)t * plane * km + col;
+  Pair<T>* R2 = reinterpret_cast<Pair<T>*>(p.R2) + (long)t * plane * km + col;
   T* delp = p.delp + (long)t * plane * km + col;
   const int ipl = (int)plane, ipe = (int)pe_ld1;  // 32-bit offsets inside a column (see remap3_column)
   auto PE1 = [&](int k) -> T { return pe[(k - 1) * ipe]; };
@@ -86,14 +86,14 @@ template <class T> FV3T_HD void remap_coef_column(const Remap3Params<T>& p, int 
     const T p2b = PE2(k + 1);
     const T dp2 = p2b - p2a;
     delp[(k - 1) * ipl] = dp2;
-    R2[(k - 1) * ipl] = T(1) / dp2;
+    R2[(k - 1) * ipl] = Pair<T>{T(1) / dp2, p2b};
     p2a = p2b;
   }
 }
 
 // ---- one column of one tracer; AK = abs(kord) -----------------------------------------------------------------------------
 template <class T, int AK, bool MAPN, int KM>
-FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp, T* ring, int rstride, int t, int i, int j, int iq) {
+FV3T_HD void remap3_column(const Remap3Params<T>& p, Pair<T>* ring, int rstride, int t, int i, int j, int iq) {
   const int n = p.n, km = p.km;
   const long nd = n + 6, plane = nd * nd;
   const T r3 = K<T>::r3(), r23 = K<T>::r23();
@@ -109,11 +109,9 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   const Pair<T>* P1 = p.P1 + (long)t * plane * (km + 1) + col;
   const T* GAM = p.GAM + (long)t * plane * (km + 1) + col;
   const T* RD1 = p.RD1 + (long)t * plane * km + col;
-  const T* R2 = p.R2 + (long)t * plane * km + col;
+  const Pair<T>* R2 = reinterpret_cast<const Pair<T>*>(p.R2) + (long)t * plane * km + col;
   auto A1 = [&](int k) -> T { return qs[(k - 1) * ipl]; };
   auto PE1 = [&](int k) -> T { return pe[(k - 1) * ipe]; };
-  const T ps = PE1(km + 1);
-  auto PE2 = [&](int k) -> T { return k == 1 ? p.ptop : (k == km + 1 ? ps : add_rn(akp[k - 1], mul_rn(bkp[k - 1], ps))); };  // uncontracted: delp is caller-visible
 
   T qv[KM + 2];
 
@@ -216,35 +214,29 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
   T c_0 = qv[1], c_p1 = qv[2], c_p2 = qv[3];
   T g_m1 = T(0), g_0 = T(0), g_p1 = a_p1 - a_0, g_p2 = a_p2 - a_p1;
   int f_m = 0, f_0 = 0, f_p = layer_flags<T>(AK, a_p1, c_p1, c_p2, g_p1, g_p2);
-  T qsum = T(0), xa = T(0), xb = T(0), sum0 = T(0), sum1 = T(0);
+  T qsum = T(0), xa = T(0), xb = T(0);
   bool zfix = false;
   int k = 1;
-  T pe2k = PE2(1), pe2k1 = PE2(2);
-  T dpk = pe2k1 - pe2k, dpk_m1 = T(0), dpk_m2 = T(0);
-  // 1/dp2 of the target layers reaches the thread through a four-deep cp.async ring (slot = k mod 4, stride `rstride`
-  // elements between slots): requested three target layers ahead, completed with cp.async.wait_group.  As a plain load it
-  // was the largest stall site (24 % of all stall samples on `qsum * rdpk`); rotated through registers two layers ahead it
+  // {1/dp2(k), pe2(k+1)} of the target layers reaches the thread through a four-deep cp.async ring (slot = k mod 4, stride
+  // `rstride` Pairs between slots): requested three target layers ahead, completed with cp.async.wait_group.  As a plain load
+  // 1/dp2 was the largest stall site (24 % of all stall samples on `qsum * rdpk`); rotated through registers two layers ahead it
   // still cost 14 % because the compiler copies the freshly loaded register at the loop join and that copy waits at once.
+  // pe2 = ak + bk*ps rides along (k_remap_coef3 evaluates it once per column, uncontracted), so the loop evaluates none.
   auto r2_request = [&](int kk) {  // target layer kk (1-based), clamped
     const int kc = kk <= km ? kk : km;
-    async_copy<sizeof(T)>(ring + (kk & 3) * rstride, R2 + (kc - 1) * ipl);
+    async_copy<sizeof(Pair<T>)>(ring + (kk & 3) * rstride, R2 + (kc - 1) * ipl);
     async_commit();
   };
   r2_request(1);
   r2_request(2);
   r2_request(3);
   async_wait_pending<2>();
-  T rdpk = ring[(1 & 3) * rstride];
+  T pe2k = p.ptop;
+  T rdpk = ring[(1 & 3) * rstride].a, pe2k1 = ring[(1 & 3) * rstride].b;
+  T dpk = pe2k1 - pe2k, dpk_m1 = T(0), dpk_m2 = T(0);
   bool started = false;
 
-  auto finalize = [&](int kk, T x, T dpkk) {
-    qd[(kk - 1) * ipl] = x;
-    if (kk >= 2) {
-      const T m = x * dpkk;
-      sum0 = sum0 + m;
-      sum1 = sum1 + f_max(T(0), m);
-    }
-  };
+  auto finalize = [&](int kk, T x) { qd[(kk - 1) * ipl] = x; };  // the fillz sums are taken only where they are needed (below)
   // value v of target layer k -> fillz pipeline (fv_fill.F90:86-128) or straight to memory
   auto emit = [&](T v) {
     if (!p.fill) {
@@ -272,7 +264,7 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
           xb = xb + dq / dpk_m1;
         }
       }
-      finalize(k - 2, xa, dpk_m2);
+      finalize(k - 2, xa);
       xa = xb;
       xb = xc;
       if (k == km) {
@@ -284,20 +276,21 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
           xa = xa - dup / dpk_m1;
           xb = xb + dup / dpk;
         }
-        finalize(km - 1, xa, dpk_m1);
-        finalize(km, xb, dpk);
+        finalize(km - 1, xa);
+        finalize(km, xb);
       }
     }
     ++k;
     if (k <= km) {
       pe2k = pe2k1;
-      pe2k1 = PE2(k + 1);
       dpk_m2 = dpk_m1;
       dpk_m1 = dpk;
-      dpk = pe2k1 - pe2k;
       r2_request(k + 2);
-      async_wait_pending<2>();  // at most the requests for k+1, k+2 are still in flight: 1/dp2(k) has landed
-      rdpk = ring[(k & 3) * rstride];
+      async_wait_pending<2>();  // at most the requests for k+1, k+2 are still in flight: slot k has landed
+      const Pair<T> r2k = ring[(k & 3) * rstride];
+      rdpk = r2k.a;
+      pe2k1 = r2k.b;
+      dpk = pe2k1 - pe2k;
     }
   };
 
@@ -405,12 +398,22 @@ FV3T_HD void remap3_column(const Remap3Params<T>& p, const T* akp, const T* bkp,
     }
   }
   // ---- fillz non-local rescale for the flagged columns (fv_fill.F90:131-152); re-reads this thread's own output
-  if (p.fill && zfix && sum0 > T(0)) {
-    const T fac = sum0 / sum1;
+  //      the two sums are taken here, in the reference's order, instead of in every column
+  if (p.fill && zfix) {
+    const T* dp2 = p.delp + (long)t * plane * km + col;  // written by k_remap_coef3
+    T sum0 = T(0), sum1 = T(0);
     for (int kk = 2; kk <= km; ++kk) {
-      const T dp = PE2(kk + 1) - PE2(kk);
-      const T x = qd[(kk - 1) * ipl];
-      qd[(kk - 1) * ipl] = f_max(T(0), fac * (x * dp) / dp);
+      const T m = qd[(kk - 1) * ipl] * dp2[(kk - 1) * ipl];
+      sum0 = sum0 + m;
+      sum1 = sum1 + f_max(T(0), m);
+    }
+    if (sum0 > T(0)) {
+      const T fac = sum0 / sum1;
+      for (int kk = 2; kk <= km; ++kk) {
+        const T dp = dp2[(kk - 1) * ipl];
+        const T x = qd[(kk - 1) * ipl];
+        qd[(kk - 1) * ipl] = f_max(T(0), fac * (x * dp) / dp);
+      }
     }
   }
 }
@@ -423,20 +426,13 @@ template <class T> __global__ void __launch_bounds__(128) k_remap_coef3(const Re
   remap_coef_column<T>(p, blockIdx.y, c % p.n + 1, c / p.n + 1);
 }
 template <class T, int AK, bool MAPN, int KM, int MINB> __global__ void __launch_bounds__(128, MINB) k_remap3(const Remap3Params<T> p) {
-  // ak, bk in shared memory: pe2(k) = ak + bk*ps sits on the dependent path of the target-layer loop
-  __shared__ T s_ak[KM + 1], s_bk[KM + 1];
-  __shared__ __align__(16) T s_ring[4 * 128];
-  for (int k = threadIdx.x; k <= p.km; k += blockDim.x) {
-    s_ak[k] = p.ak[k];
-    s_bk[k] = p.bk[k];
-  }
-  __syncthreads();
+  __shared__ __align__(16) Pair<T> s_ring[4 * 128];
   const int cols = p.n * p.n;
   // blockIdx.x = tracer: the nq CTAs of one column block are adjacent in the grid, run together and share P1, GAM, RD1, R2, pe
   // through L2 (with the tracer as the slowest index every tracer streamed them from HBM again: 64 of 121 B per update)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  remap3_column<T, AK, MAPN, KM>(p, s_ak, s_bk, s_ring + threadIdx.x, 128, blockIdx.z, c % p.n + 1, c / p.n + 1, p.iq0 + blockIdx.x);
+  remap3_column<T, AK, MAPN, KM>(p, s_ring + threadIdx.x, 128, blockIdx.z, c % p.n + 1, c / p.n + 1, p.iq0 + blockIdx.x);
 }
 #endif
 

@@ -87,12 +87,20 @@ def sim3():
     so = os.path.join(SIM, "libhostsim_remap3.so")
     src = os.path.join(SIM, "remap3_hostsim.cu")
     csrc = os.path.join(HERE, "..", "fv3atm_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fv3t_remap3.cuh", "fv3t_remap2.cuh", "fv3t_remap.cuh", "fv3t_common.cuh",
+    deps = [src] + [os.path.join(csrc, f) for f in ("fv3t_remap5.cuh", "fv3t_remap3.cuh", "fv3t_remap2.cuh", "fv3t_remap.cuh", "fv3t_common.cuh",
                                                      "fv3t_advect3.cuh", "fv3t_advect4.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["nvcc", "-x", "cu", "-O2", "-std=c++17", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC,-fno-fast-math", "-shared", "-o", so, src], check=True, cwd=SIM)
     return C.CDLL(so)
+
+
+@pytest.fixture(params=[3, 5], ids=["three-walk", "two-walk"])
+def variant(request, sim3):
+    """k_remap3's column routine / k_remap5's (bottom-up elimination, fv3t_remap5.cuh)"""
+    sim3.hostsim_remap_variant(request.param)
+    yield request.param
+    sim3.hostsim_remap_variant(3)
 
 
 def run_sim3(sim3, q, pe, ak, bk, ptop, akord, fill):
@@ -114,7 +122,7 @@ def run_sim3(sim3, q, pe, ak, bk, ptop, akord, fill):
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("kord", [9, 8, 12, 13, 14, 17])
-def test_fast_remap_matches_oracle(sim3, oracle, case_factory, kord, dtype):
+def test_fast_remap_matches_oracle(sim3, oracle, case_factory, kord, dtype, variant):
     """The limiters the product runs on the fast path (fv3t::fast_kord_ok).  kord 10, 11, 15, 16 compare COMPUTED interface
     values (ext5 / ext6, fv_mapz.F90:1820-1846) that are exactly equal on flat data, so any re-association flips them: the
     product keeps those on its bit-exact strict kernel."""
@@ -129,7 +137,7 @@ def test_fast_remap_matches_oracle(sim3, oracle, case_factory, kord, dtype):
     assert (d / np.maximum(s, 1e-300)).max() <= tol, d / s
 
 
-def test_fast_remap_fillz_and_conservation(sim3, oracle, case_factory):
+def test_fast_remap_fillz_and_conservation(sim3, oracle, case_factory, variant):
     """Signed tracer: every fillz branch; and the column integral sum(q*dp) is conserved by the remap without fill."""
     case = case_factory(12, 32, 9, "float64")
     q0 = np.array(case.q, copy=True)
