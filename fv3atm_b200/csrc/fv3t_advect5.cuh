@@ -61,6 +61,19 @@ template <class T> struct A5Stage {
   static size_t smem_bytes(int tg) { return (size_t)GROUP_OFF + (size_t)tg * GROUP_ELEMS * sizeof(T); }
 };
 
+// Sub-tile contexts (a rank that owns PART of a cubed-sphere tile, fv_arrays.F90:1178-1186 with layout > 1x1): the resident
+// "tile" is a square sub-domain; the tile-edge formulas of xppm / yppm apply only on the sides that lie on a tile edge and the
+// corner views of copy_corners only at true tile corners (gridstruct%sw_corner .., fv_arrays.F90:181) -- everywhere else the
+// halo holds the neighbouring sub-domain's cells (diagonal neighbours included) and the interior formulas apply.
+// The PPM element functions select the edge formulas by index against 1 and npx: a missing west / south edge is expressed by
+// SHIFTING the index they see (and the accessors back) by A5_SHIFT, a missing east / north edge by an unreachable npx.
+struct A5Sub {
+  int no_w = 0, no_e = 0, no_s = 0, no_n = 0;  // 1: that side of the resident square is NOT a tile edge
+  int cmask = 15;                              // true tile corners: 1 SW, 2 SE, 4 NE, 8 NW
+};
+constexpr int A5_SHIFT = 1 << 20;
+constexpr int A5_NOEDGE = 1 << 28;
+
 struct alignas(64) Adv5Maps {
   CUtensorMap x2, y2, cab, rx, ry, mfx, mfy, area, rarea;
 };
@@ -79,6 +92,7 @@ template <class T> struct Adv5Params {
   int tg;               // tracers per CTA (block = 32 + 64*tg threads)
   int iq0, nql;         // this launch advects tracers iq0 .. iq0+nql-1
   T lim_fac;
+  A5Sub sub[6];         // per resident tile; the default is a whole tile
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -204,6 +218,7 @@ template <class T> __global__ void __launch_bounds__(256) k_pad_plane(T* __restr
 // ---------------------------------------------------------------------------------------------------------------------
 struct Adv5Cta {  // uniform over one tracer group
   int n, npx, nd, i0, nw, gb;
+  int shx, nxx, shy, nyy, cmask;  // index shift / edge position seen by the PPM element functions in x and y; true corners (A5Sub)
   int tile, tileoff;  // element offset of this tile in the Fortran-layout 2-D metric arrays
   long qoff;          // element offset of the (tile, tracer, level) plane of q
   bool xedge;         // the strip touches the west or east tile edge
@@ -224,8 +239,14 @@ template <class T> FV3T_HD bool adv5_make_cta(const Adv5Params<T>& p, int strip,
   c.tile = t;
   c.tileoff = t * nd * nd;
   c.qoff = (((long)t * p.nq + iq) * npz + kz) * (long)nd * nd;
+  const A5Sub sb = p.sub[t];
+  c.shx = sb.no_w ? A5_SHIFT : 0;
+  c.nxx = sb.no_e ? A5_NOEDGE : c.npx + c.shx;
+  c.shy = sb.no_s ? A5_SHIFT : 0;
+  c.nyy = sb.no_n ? A5_NOEDGE : c.npx + c.shy;
+  c.cmask = sb.cmask;
   // x-faces i0 .. i0+nw evaluate cells i0-1 .. i0+nw; the tile-edge formulas apply to cells <= 2 and >= npx-2
-  c.xedge = (c.i0 - 1 <= 2) || (c.i0 + c.nw >= c.npx - 2);
+  c.xedge = (!sb.no_w && c.i0 - 1 <= 2) || (!sb.no_e && c.i0 + c.nw >= c.npx - 2);
   return true;
 }
 
@@ -299,7 +320,8 @@ FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3T
     r = r > n + 3 ? n + 3 : r;
     const int i = t.i;
     int ox = (r + 2) * nd, oy = ox;
-    if (t.icor && (r < 1 || r > n) && i <= n + 3) {
+    const int cbit = r < 1 ? (i < 1 ? 1 : 2) : (i > n ? 4 : 8);
+    if (t.icor && (r < 1 || r > n) && i <= n + 3 && (c.cmask & cbit)) {
       int s1i, s1j, s2i, s2j;
       if (i < 1 && r < 1) {  // SW
         s1i = r, s1j = 1 - i, s2i = 1 - r, s2j = i;
@@ -335,11 +357,12 @@ FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int cc = r - 2;
   const Pair<T> y2 = A5P(v, A5_Y2, PH);  // zero outside the faces 1..n+1 (k_prep5, TMA zero fill)
   const T* dya = p.dya + c.tileoff + t.pix;
-  auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
+  const int shy = c.shy;
+  auto met_y = [&](int row) -> T { return dya[(row - shy + 2) * nd]; };
   T qy = A5XROW(s, A5X_Q + PH)[0];
   if (YE && (r < 1 || r > c.n)) qy = s.qys[(A5V_QY + PH) * A5_GW];
   const T q_o = s.yin.template q_cm1<PH>();
-  const T fy2_c = s.yin.template push<PH, YE>(cc, qy, y2.a, c.npx, p.lim_fac, met_y, s.qys + A5V_EIN * A5_GW, A5_GW);
+  const T fy2_c = s.yin.template push<PH, YE>(cc + shy, qy, y2.a, c.nyy, p.lim_fac, met_y, s.qys + A5V_EIN * A5_GW, A5_GW);
   const T Fy_c = y2.b * fy2_c;
   T qi;  // only rows o = 1..n are consumed
   if (EX) {
@@ -359,16 +382,16 @@ FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
-  const int i = t.i;
-  const T* dxa = p.dxa + c.tileoff + 2;
+  const int i = t.i + c.shx;  // the column index the PPM functions see (A5Sub); the accessors take the same shifted index
+  const T* dxa = p.dxa + c.tileoff + 2 - c.shx;
   auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
-  const T* sqa = A5XROW(s, A5X_Q + PH) - i;  // indexable by the global column
+  const T* sqa = A5XROW(s, A5X_Q + PH) - i;  // indexable by the (shifted) column
   const T* sqb = A5XROW(s, A5X_QI + (PH & 1)) - i;
   auto qa = [&](int gi) -> T { return sqa[gi]; };
   auto qb = [&](int gi) -> T { return sqb[gi]; };
-  A5XROW(s, A5X_DR)[0] = ppm_pre<T, OI, XE>(i, c.npx, qa, dxa_r);
-  A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, c.npx, qb, dxa_o);
+  A5XROW(s, A5X_DR)[0] = ppm_pre<T, OI, XE>(i, c.nxx, qa, dxa_r);
+  A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, c.nxx, qb, dxa_o);
 }
 
 template <class T, int OI, int OO, int PH, bool XE, bool EX = false>
@@ -376,8 +399,8 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
-  const int i = t.i;
-  const T* dxa = p.dxa + c.tileoff + 2;
+  const int i = t.i + c.shx;
+  const T* dxa = p.dxa + c.tileoff + 2 - c.shx;
   auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
   const T *sqa = A5XROW(s, A5X_Q + PH) - i, *sda = A5XROW(s, A5X_DR) - i, *sqb = A5XROW(s, A5X_QI + (PH & 1)) - i, *sdb = A5XROW(s, A5X_DO) - i;
@@ -386,9 +409,9 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   auto qb = [&](int gi) -> T { return sqb[gi]; };
   auto ab = [&](int gi) -> T { return sdb[gi]; };
   const Pair<T> x2r = A5P(v, A5_XR, PH);
-  const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, c.npx, p.lim_fac, qa, aa, dxa_r);
+  const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, c.nxx, p.lim_fac, qa, aa, dxa_r);
   A5XROW(s, A5X_SF1)[0] = x2r.b * fx2;
-  const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, c.npx, p.lim_fac, qb, ab, dxa_o);
+  const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, c.nxx, p.lim_fac, qb, ab, dxa_o);
   const T fx2o = s.qys[(A5V_FX2 + ((PH + 1) & 3)) * A5_GW];  // fx2 of row r-3, stored three row steps ago
   A5XROW(s, A5X_SFT)[0] = EX ? T(0.5) * (fxo + fx2o) * A5S(v, A5_MFX, PH) : (fxo + fx2o) * A5S(v, A5_MFX, PH);
   s.qys[(A5V_FX2 + PH) * A5_GW] = fx2;
@@ -399,7 +422,8 @@ FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int n = c.n, nd = c.nd;
   const int cc = r - 2, o = r - 3;
   const T* dya = p.dya + c.tileoff + t.pix;
-  auto met_y = [&](int row) -> T { return dya[(row + 2) * nd]; };
+  const int shy = c.shy;
+  auto met_y = [&](int row) -> T { return dya[(row - shy + 2) * nd]; };
   const T* sf1 = A5XROW(s, A5X_SF1);
   const T* sft = A5XROW(s, A5X_SFT);
   const T qx = A5XROW(s, A5X_Q + PH)[0];
@@ -411,7 +435,7 @@ FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   } else {
     qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) * A5S(v, A5_RX, PH);
   }
-  const T fyo_c = s.you.template push<PH, YE>(cc, qj, A5P(v, A5_Y2, PH).a, c.npx, p.lim_fac, met_y, s.qys + A5V_EOU * A5_GW, A5_GW);
+  const T fyo_c = s.you.template push<PH, YE>(cc + shy, qj, A5P(v, A5_Y2, PH).a, c.nyy, p.lim_fac, met_y, s.qys + A5V_EOU * A5_GW, A5_GW);
   const T fy2c = s.qys[(A5V_FY2 + (PH & 1)) * A5_GW];
   const T fys_c = EX ? T(0.5) * (fyo_c + fy2c) * A5S(v, A5_MFY, PH) : (fyo_c + fy2c) * A5S(v, A5_MFY, PH);  // mfy: zero outside faces 1..n+1
   const Pair<T> ab = A5P(v, A5_CAB, PH);

@@ -144,8 +144,9 @@ template <class T, bool EX> static int dispatch(const Adv5Params<T>& p, int hord
 template <class T>
 static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area, const T* rarea,
                          const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, const int64_t* halo_dst,
-                         const int64_t* halo_src, int64_t halo_len, int hord, T lim_fac, int nsplt, const int* ksplt, int exact) {
-  const int nt = 6, nd = n + 6, PP = a5_pitch(n);
+                         const int64_t* halo_src, int64_t halo_len, int hord, T lim_fac, int nsplt, const int* ksplt, int exact,
+                         int nt = 6, const int* sub = nullptr) {
+  const int nd = n + 6, PP = a5_pitch(n);
   const long plane = (long)nd * nd;
   const size_t nlev = (size_t)nt * npz, pe = nlev * nd * PP;
   std::vector<Pair<T>> X2(pe, Pair<T>{T(0), T(0)}), Y2(pe, Pair<T>{T(0), T(0)}), CAB(pe, Pair<T>{T(0), T(0)});
@@ -169,32 +170,37 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
         const int64_t d = halo_dst[e], s = halo_src[e];
         q[(d / plane) * tile_stride + pl * plane + d % plane] = q[(s / plane) * tile_stride + pl * plane + s % plane];
       }
-    Adv5Params<T> p{};
-    p.qin = q;
-    p.qout = qb.data();
-    p.X2 = X2.data();
-    p.Y2 = Y2.data();
-    p.CAB = CAB.data();
-    p.RX = RX.data();
-    p.RY = RY.data();
-    p.MFX = MX.data();
-    p.MFY = MY.data();
-    p.AREA = AREA.data();
-    p.RAREA = RAREA.data();
-    p.dxa = dxa;
-    p.dya = dya;
-    p.ksplt = ksplt;
-    p.n = n;
-    p.npz = npz;
-    p.nq = nq;
-    p.ntiles = nt;
-    p.it = it;
-    p.lev0 = 0;
-    p.tg = 1;
-    p.iq0 = 0;
-    p.nql = nq;
-    p.lim_fac = lim_fac;
-    if (exact ? dispatch<T, true>(p, hord) : dispatch<T, false>(p, hord)) return 1;
+    // one resident "tile" (whole tile or sub-domain) at a time: Adv5Params carries the flags of at most six
+    for (int t = 0; t < nt; ++t) {
+      const size_t so = (size_t)t * npz * nd * PP;
+      Adv5Params<T> p{};
+      p.qin = q + (size_t)t * tile_stride;
+      p.qout = qb.data() + (size_t)t * tile_stride;
+      p.X2 = X2.data() + so;
+      p.Y2 = Y2.data() + so;
+      p.CAB = CAB.data() + so;
+      p.RX = RX.data() + so;
+      p.RY = RY.data() + so;
+      p.MFX = MX.data() + so;
+      p.MFY = MY.data() + so;
+      p.AREA = AREA.data() + (size_t)t * nd * PP;
+      p.RAREA = RAREA.data() + (size_t)t * nd * PP;
+      p.dxa = dxa + (size_t)t * plane;
+      p.dya = dya + (size_t)t * plane;
+      p.ksplt = ksplt;
+      p.n = n;
+      p.npz = npz;
+      p.nq = nq;
+      p.ntiles = 1;
+      p.it = it;
+      p.lev0 = 0;
+      p.tg = 1;
+      p.iq0 = 0;
+      p.nql = nq;
+      p.lim_fac = lim_fac;
+      if (sub) p.sub[0] = A5Sub{sub[5 * t], sub[5 * t + 1], sub[5 * t + 2], sub[5 * t + 3], sub[5 * t + 4]};
+      if (exact ? dispatch<T, true>(p, hord) : dispatch<T, false>(p, hord)) return 1;
+    }
     for (int t = 0; t < nt; ++t)
       for (int iq = 0; iq < nq; ++iq)
         for (int kz = 0; kz < npz; ++kz) {
@@ -222,6 +228,15 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
   return 0;
 }
 
+#define API_SUB(T, S)                                                                                                          \
+  extern "C" int hostsim5_tracer_2d_sub_##S(int nt, int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy,        \
+                                            const T* area, const T* rarea, const T* dx, const T* dy, const T* dxa,             \
+                                            const T* dya, const T* sin_sg, const int64_t* halo_dst, const int64_t* halo_src,   \
+                                            int64_t halo_len, int hord, T lim_fac, int nsplt, const int* ksplt, int exact,     \
+                                            const int* sub) {                                                                  \
+    return tracer_2d_sim<T>(n, npz, nq, q, dp1, mfx, mfy, cx, cy, area, rarea, dx, dy, dxa, dya, sin_sg, halo_dst, halo_src,  \
+                            halo_len, hord, lim_fac, nsplt, ksplt, exact, nt, sub);                                            \
+  }
 #define API(T, S)                                                                                                              \
   extern "C" int hostsim5_tracer_2d_##S(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T* cx, T* cy, const T* area,     \
                                         const T* rarea, const T* dx, const T* dy, const T* dxa, const T* dya, const T* sin_sg, \
@@ -232,3 +247,5 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
   }
 API(double, f64)
 API(float, f32)
+API_SUB(double, f64)
+API_SUB(float, f32)

@@ -105,3 +105,85 @@ def test_advect5_interior_strips_and_blocks(sim5, oracle, case_factory, dtype):
     got = run_sim(sim5, case, 8, ref, exact=True)
     sl = slice(NG, -NG)
     assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl])
+
+
+# ---- sub-tile decomposition (layout L x L per tile): edge formulas on true tile edges only, corner views at true cube corners only,
+#      halos (incl. the diagonal blocks) from the neighbouring sub-domains -----------------------------------------------------------
+def run_sim_sub(sim, case, hord, ref, L, exact, lim_fac=1.0):
+    """The same tracer_2d through the host-simulated kernels, one L x L sub-domain mosaic: returns q on the whole tiles."""
+    from fv3atm_b200.subdomain import SubMosaic
+    sfx, ct = ("f64", C.c_double) if case.dtype == np.float64 else ("f32", C.c_float)
+    mo = SubMosaic(case.n, L)
+    ns, m = len(mo), mo.m
+    g = case.metrics()
+    st = lambda f, a: np.ascontiguousarray(np.stack([f(a, s) for s in range(ns)]))
+    q = st(mo.cells, case.q)
+    dp1 = st(mo.cells, case.dp1)
+    cx, cy = st(mo.xface, case.cx), st(mo.yface, case.cy)
+    mfx, mfy = st(mo.mfx, case.mfx), st(mo.mfy, case.mfy)
+    gm = {k: st(mo.cells, g[k]) for k in ("area", "rarea", "dxa", "dya", "sin_sg")}
+    gm["dx"], gm["dy"] = st(mo.dx, g["dx"]), st(mo.dy, g["dy"])
+    ds, do, ss, so = mo.halo_table()
+    plane = (m + 6) * (m + 6)
+    dst = np.ascontiguousarray(ds * plane + do)
+    src = np.ascontiguousarray(ss * plane + so)
+    sub = np.ascontiguousarray(np.array([mo.flags(s) for s in range(ns)], dtype=np.int32))
+    ksplt = np.ascontiguousarray(ref["ksplt"], dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = getattr(sim, f"hostsim5_tracer_2d_sub_{sfx}")(
+        ns, m, case.npz, case.nq, p(q), p(dp1), p(mfx), p(mfy), p(cx), p(cy), p(gm["area"]), p(gm["rarea"]), p(gm["dx"]), p(gm["dy"]),
+        p(gm["dxa"]), p(gm["dya"]), p(gm["sin_sg"]), p(dst), p(src), C.c_int64(dst.size), int(hord), ct(lim_fac), int(ref["nsplt"]),
+        p(ksplt), int(bool(exact)), p(sub))
+    assert rc == 0
+    qw = np.array(case.q, copy=True)
+    dw = np.array(case.dp1, copy=True)
+    for s in range(ns):
+        mo.put_interior(qw, s, q[s])
+        mo.put_interior(dw, s, dp1[s])
+    return {"q": qw, "dp1": dw}
+
+
+def test_submosaic_halo_table_reproduces_the_whole_tile_exchange(case_factory):
+    """Scattering a field to sub-domains, exchanging with the gather lists and reading the halos back gives exactly what the
+    whole-tile exchange gives -- on every halo cell that is not part of a true cube-corner block, diagonal blocks included."""
+    from fv3atm_b200 import cubed_sphere as cs
+    from fv3atm_b200.subdomain import SubMosaic
+    n = 24
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((6, 2, n + 6, n + 6))
+    a[:, :, :3, :] = a[:, :, -3:, :] = a[:, :, :, :3] = a[:, :, :, -3:] = np.nan
+    whole = cs.fill_edge_halos(a.copy(), n)
+    for L in (2, 3):
+        mo = SubMosaic(n, L)
+        m = mo.m
+        stack = np.stack([mo.cells(a, s) for s in range(len(mo))])
+        interior = np.zeros((m + 6, m + 6), bool)
+        interior[3:-3, 3:-3] = True
+        stack[:, :, ~interior] = np.nan
+        mo.fill_halos(stack)
+        for s in range(len(mo)):
+            want = mo.cells(whole, s)
+            ok = ~np.isnan(want)
+            assert np.array_equal(stack[s][ok], want[ok])
+            assert np.isnan(stack[s][~ok]).all()            # true corner blocks stay untouched
+            w, e, so_, no, cmask = mo.flags(s)
+            assert (~ok[0]).sum() == 9 * bin(cmask).count("1")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("hord,exact", [(8, False), (10, True), (5, True), (13, True), (-5, True)])
+@pytest.mark.parametrize("L", [2, 3])
+def test_advect5_submosaic_is_bit_identical_to_whole_tiles(sim5, oracle, case_factory, hord, exact, L, dtype):
+    """layout L x L: every sub-domain runs the same kernels with its own edge / corner flags and exchanged halos; the assembled
+    field must equal the whole-tile run bit for bit (the per-cell arithmetic does not depend on the decomposition), with
+    sub-stepping (two exchanges)."""
+    case = case_factory(24, 4, 5, dtype, courant=1.8)
+    ref = oracle.tracer_2d(case, hord=hord)
+    assert ref["nsplt"] >= 2
+    whole = run_sim(sim5, case, hord, ref, exact=exact)
+    got = run_sim_sub(sim5, case, hord, ref, L, exact)
+    sl = slice(NG, -NG)
+    assert np.array_equal(got["q"][..., sl, sl], whole["q"][..., sl, sl]), norm_diff(got["q"], whole["q"])
+    assert np.array_equal(got["dp1"][..., sl, sl], whole["dp1"][..., sl, sl])
+    if exact:
+        assert np.array_equal(got["q"][..., sl, sl], ref["q"][..., sl, sl])
