@@ -218,11 +218,20 @@ template <class T> __global__ void __launch_bounds__(256) k_pad_plane(T* __restr
 // ---------------------------------------------------------------------------------------------------------------------
 struct Adv5Cta {  // uniform over one tracer group
   int n, npx, nd, i0, nw, gb;
-  int shx, nxx, shy, nyy, cmask;  // index shift / edge position seen by the PPM element functions in x and y; true corners (A5Sub)
   int tile, tileoff;  // element offset of this tile in the Fortran-layout 2-D metric arrays
   long qoff;          // element offset of the (tile, tracer, level) plane of q
   bool xedge;         // the strip touches the west or east tile edge
 };
+
+// index shift / edge position the PPM element functions see in x and in y (A5Sub); EDGE = false: nothing looks at them
+template <class T, bool EDGE> FV3T_HD int a5_shift_x(const Adv5Params<T>& p, const Adv5Cta& c) { return EDGE && p.sub[c.tile].no_w ? A5_SHIFT : 0; }
+template <class T, bool EDGE> FV3T_HD int a5_shift_y(const Adv5Params<T>& p, const Adv5Cta& c) { return EDGE && p.sub[c.tile].no_s ? A5_SHIFT : 0; }
+template <class T, bool EDGE> FV3T_HD int a5_edge_x(const Adv5Params<T>& p, const Adv5Cta& c, int sh) {
+  return EDGE && p.sub[c.tile].no_e ? A5_NOEDGE : c.npx + sh;
+}
+template <class T, bool EDGE> FV3T_HD int a5_edge_y(const Adv5Params<T>& p, const Adv5Cta& c, int sh) {
+  return EDGE && p.sub[c.tile].no_n ? A5_NOEDGE : c.npx + sh;
+}
 
 template <class T> FV3T_HD bool adv5_make_cta(const Adv5Params<T>& p, int strip, int levc, int iq, Adv5Cta& c) {
   const int n = p.n, npz = p.npz;
@@ -239,12 +248,9 @@ template <class T> FV3T_HD bool adv5_make_cta(const Adv5Params<T>& p, int strip,
   c.tile = t;
   c.tileoff = t * nd * nd;
   c.qoff = (((long)t * p.nq + iq) * npz + kz) * (long)nd * nd;
+  // (the flags of a sub-tile context are read from the kernel parameters where the EDGE instantiations need them -- a5_shift_* --
+  // and not carried in registers: the interior blocks, which never look at them, are the ones that set the register budget)
   const A5Sub sb = p.sub[t];
-  c.shx = sb.no_w ? A5_SHIFT : 0;
-  c.nxx = sb.no_e ? A5_NOEDGE : c.npx + c.shx;
-  c.shy = sb.no_s ? A5_SHIFT : 0;
-  c.nyy = sb.no_n ? A5_NOEDGE : c.npx + c.shy;
-  c.cmask = sb.cmask;
   // x-faces i0 .. i0+nw evaluate cells i0-1 .. i0+nw; the tile-edge formulas apply to cells <= 2 and >= npx-2
   c.xedge = (!sb.no_w && c.i0 - 1 <= 2) || (!sb.no_e && c.i0 + c.nw >= c.npx - 2);
   return true;
@@ -312,7 +318,7 @@ FV3T_HD void adv5_init(const Adv5Params<T>& p, const Adv5Cta& c, const Adv3Thr& 
 // view into the private slot (the x sweeps see the dir = 1 corner view of q, the y sweeps the dir = 2 view: copy_corners,
 // tp_core.F90:265-328)
 template <class T, int OI, int OO, int PH, bool CORNER>
-FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+FV3T_HD void adv5_issue_q(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd, npx = c.npx;
   if (!CORNER) {
     async_copy<sizeof(T)>(A5XROW(s, A5X_Q + PH), s.qg + (r + 2) * nd);
@@ -321,7 +327,7 @@ FV3T_HD void adv5_issue_q(const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3T
     const int i = t.i;
     int ox = (r + 2) * nd, oy = ox;
     const int cbit = r < 1 ? (i < 1 ? 1 : 2) : (i > n ? 4 : 8);
-    if (t.icor && (r < 1 || r > n) && i <= n + 3 && (c.cmask & cbit)) {
+    if (t.icor && (r < 1 || r > n) && i <= n + 3 && (p.sub[c.tile].cmask & cbit)) {
       int s1i, s1j, s2i, s2j;
       if (i < 1 && r < 1) {  // SW
         s1i = r, s1j = 1 - i, s2i = 1 - r, s2j = i;
@@ -357,12 +363,12 @@ FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int cc = r - 2;
   const Pair<T> y2 = A5P(v, A5_Y2, PH);  // zero outside the faces 1..n+1 (k_prep5, TMA zero fill)
   const T* dya = p.dya + c.tileoff + t.pix;
-  const int shy = c.shy;
+  const int shy = a5_shift_y<T, YE>(p, c);
   auto met_y = [&](int row) -> T { return dya[(row - shy + 2) * nd]; };
   T qy = A5XROW(s, A5X_Q + PH)[0];
   if (YE && (r < 1 || r > c.n)) qy = s.qys[(A5V_QY + PH) * A5_GW];
   const T q_o = s.yin.template q_cm1<PH>();
-  const T fy2_c = s.yin.template push<PH, YE>(cc + shy, qy, y2.a, c.nyy, p.lim_fac, met_y, s.qys + A5V_EIN * A5_GW, A5_GW);
+  const T fy2_c = s.yin.template push<PH, YE>(cc + shy, qy, y2.a, a5_edge_y<T, YE>(p, c, shy), p.lim_fac, met_y, s.qys + A5V_EIN * A5_GW, A5_GW);
   const T Fy_c = y2.b * fy2_c;
   T qi;  // only rows o = 1..n are consumed
   if (EX) {
@@ -382,16 +388,17 @@ FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
-  const int i = t.i + c.shx;  // the column index the PPM functions see (A5Sub); the accessors take the same shifted index
-  const T* dxa = p.dxa + c.tileoff + 2 - c.shx;
+  const int shx = a5_shift_x<T, XE>(p, c), nxx = a5_edge_x<T, XE>(p, c, shx);
+  const int i = t.i + shx;  // the column index the PPM functions see (A5Sub); the accessors take the same shifted index
+  const T* dxa = p.dxa + c.tileoff + 2 - shx;
   auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
   const T* sqa = A5XROW(s, A5X_Q + PH) - i;  // indexable by the (shifted) column
   const T* sqb = A5XROW(s, A5X_QI + (PH & 1)) - i;
   auto qa = [&](int gi) -> T { return sqa[gi]; };
   auto qb = [&](int gi) -> T { return sqb[gi]; };
-  A5XROW(s, A5X_DR)[0] = ppm_pre<T, OI, XE>(i, c.nxx, qa, dxa_r);
-  A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, c.nxx, qb, dxa_o);
+  A5XROW(s, A5X_DR)[0] = ppm_pre<T, OI, XE>(i, nxx, qa, dxa_r);
+  A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, nxx, qb, dxa_o);
 }
 
 template <class T, int OI, int OO, int PH, bool XE, bool EX = false>
@@ -399,8 +406,9 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
-  const int i = t.i + c.shx;
-  const T* dxa = p.dxa + c.tileoff + 2 - c.shx;
+  const int shx = a5_shift_x<T, XE>(p, c), nxx = a5_edge_x<T, XE>(p, c, shx);
+  const int i = t.i + shx;
+  const T* dxa = p.dxa + c.tileoff + 2 - shx;
   auto dxa_r = [&](int gi) -> T { return dxa[(rr + 2) * nd + gi]; };
   auto dxa_o = [&](int gi) -> T { return dxa[(o + 2) * nd + gi]; };
   const T *sqa = A5XROW(s, A5X_Q + PH) - i, *sda = A5XROW(s, A5X_DR) - i, *sqb = A5XROW(s, A5X_QI + (PH & 1)) - i, *sdb = A5XROW(s, A5X_DO) - i;
@@ -409,9 +417,9 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   auto qb = [&](int gi) -> T { return sqb[gi]; };
   auto ab = [&](int gi) -> T { return sdb[gi]; };
   const Pair<T> x2r = A5P(v, A5_XR, PH);
-  const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, c.nxx, p.lim_fac, qa, aa, dxa_r);
+  const T fx2 = xface_flux<T, OI, XE>(i, x2r.a, nxx, p.lim_fac, qa, aa, dxa_r);
   A5XROW(s, A5X_SF1)[0] = x2r.b * fx2;
-  const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, c.nxx, p.lim_fac, qb, ab, dxa_o);
+  const T fxo = xface_flux<T, OO, XE>(i, A5P(v, A5_XO, PH).a, nxx, p.lim_fac, qb, ab, dxa_o);
   const T fx2o = s.qys[(A5V_FX2 + ((PH + 1) & 3)) * A5_GW];  // fx2 of row r-3, stored three row steps ago
   A5XROW(s, A5X_SFT)[0] = EX ? T(0.5) * (fxo + fx2o) * A5S(v, A5_MFX, PH) : (fxo + fx2o) * A5S(v, A5_MFX, PH);
   s.qys[(A5V_FX2 + PH) * A5_GW] = fx2;
@@ -422,7 +430,7 @@ FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   const int n = c.n, nd = c.nd;
   const int cc = r - 2, o = r - 3;
   const T* dya = p.dya + c.tileoff + t.pix;
-  const int shy = c.shy;
+  const int shy = a5_shift_y<T, YE>(p, c);
   auto met_y = [&](int row) -> T { return dya[(row - shy + 2) * nd]; };
   const T* sf1 = A5XROW(s, A5X_SF1);
   const T* sft = A5XROW(s, A5X_SFT);
@@ -435,7 +443,7 @@ FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   } else {
     qj = (qx * A5S(v, A5_AR, PH) + sf1[0] - sf1[1]) * A5S(v, A5_RX, PH);
   }
-  const T fyo_c = s.you.template push<PH, YE>(cc + shy, qj, A5P(v, A5_Y2, PH).a, c.nyy, p.lim_fac, met_y, s.qys + A5V_EOU * A5_GW, A5_GW);
+  const T fyo_c = s.you.template push<PH, YE>(cc + shy, qj, A5P(v, A5_Y2, PH).a, a5_edge_y<T, YE>(p, c, shy), p.lim_fac, met_y, s.qys + A5V_EOU * A5_GW, A5_GW);
   const T fy2c = s.qys[(A5V_FY2 + (PH & 1)) * A5_GW];
   const T fys_c = EX ? T(0.5) * (fyo_c + fy2c) * A5S(v, A5_MFY, PH) : (fyo_c + fy2c) * A5S(v, A5_MFY, PH);  // mfy: zero outside faces 1..n+1
   const Pair<T> ab = A5P(v, A5_CAB, PH);
@@ -524,7 +532,7 @@ __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta
                                            const A5View<T>& vp, const A5View<T>& v, const unsigned char* next_stage, uint64_t* full_next,
                                            unsigned par_next, uint64_t* empty_prev, int r0, int g, int gtid) {
   // ---- step r0 (PH 0)
-  adv5_issue_q<T, OI, OO, 2, YE>(c, s, t, r0 + 2);
+  adv5_issue_q<T, OI, OO, 2, YE>(p, c, s, t, r0 + 2);
   async_wait_pending<1>();  // q of row r0+1 has landed (r0 landed one step ago)
   adv5_phase2<T, OI, OO, 0, XE>(p, c, s, t, r0);
   if (!YE || r0 > -2) adv5_phase4<T, OI, OO, 3, YE, EX>(p, c, s, t, vp, r0 - 1);
@@ -537,7 +545,7 @@ __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta
   adv5_phase1<T, OI, OO, 1, YE, EX>(p, c, s, t, v, r0 + 1);
   a5_group_sync<ONEG>(g);
   // ---- step r0+1 (PH 1)
-  adv5_issue_q<T, OI, OO, 3, YE>(c, s, t, r0 + 3);
+  adv5_issue_q<T, OI, OO, 3, YE>(p, c, s, t, r0 + 3);
   async_wait_pending<1>();
   adv5_phase2<T, OI, OO, 1, XE>(p, c, s, t, r0 + 1);
   adv5_phase4<T, OI, OO, 0, YE, EX>(p, c, s, t, v, r0);
@@ -546,7 +554,7 @@ __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta
   adv5_phase1<T, OI, OO, 2, YE, EX>(p, c, s, t, v, r0 + 2);
   a5_group_sync<ONEG>(g);
   // ---- step r0+2 (PH 2)
-  adv5_issue_q<T, OI, OO, 0, YE>(c, s, t, r0 + 4);
+  adv5_issue_q<T, OI, OO, 0, YE>(p, c, s, t, r0 + 4);
   async_wait_pending<1>();
   adv5_phase2<T, OI, OO, 2, XE>(p, c, s, t, r0 + 2);
   adv5_phase4<T, OI, OO, 1, YE, EX>(p, c, s, t, v, r0 + 1);
@@ -555,7 +563,7 @@ __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta
   adv5_phase1<T, OI, OO, 3, YE, EX>(p, c, s, t, v, r0 + 3);
   a5_group_sync<ONEG>(g);
   // ---- step r0+3 (PH 3)
-  adv5_issue_q<T, OI, OO, 1, YE>(c, s, t, r0 + 5);
+  adv5_issue_q<T, OI, OO, 1, YE>(p, c, s, t, r0 + 5);
   async_wait_pending<1>();
   adv5_phase2<T, OI, OO, 3, XE>(p, c, s, t, r0 + 3);
   adv5_phase4<T, OI, OO, 2, YE, EX>(p, c, s, t, v, r0 + 2);
@@ -636,8 +644,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ 
   T* gsm = reinterpret_cast<T*>(smem5 + S::GROUP_OFF) + (size_t)g * S::GROUP_ELEMS;
   adv5_init<T, OI, OO>(p, c, t, gsm, s);
   constexpr bool ONEG = NTHR == 32 + A5_GW;
-  adv5_issue_q<T, OI, OO, 0, true>(c, s, t, -2);
-  adv5_issue_q<T, OI, OO, 1, true>(c, s, t, -1);
+  adv5_issue_q<T, OI, OO, 0, true>(p, c, s, t, -2);
+  adv5_issue_q<T, OI, OO, 1, true>(p, c, s, t, -1);
   async_wait_all();
   a5_mbar_wait(&full[0], 0);
   const int xs = strip * A5_W;

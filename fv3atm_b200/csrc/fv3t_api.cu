@@ -164,6 +164,10 @@ template <class T> struct Impl {
   int* strip_halo[6][4] = {};
   EdgeMap maps[6][4];
   int local_of[6];  // global tile (0-based) -> local slot or -1
+  int sub_L = 0;               // sub-tile context: layout L x L per tile (0: whole tiles); flags per resident sub-domain
+  fv3t::A5Sub subflags[6];
+  std::vector<int*> lists;     // gather / scatter lists (fv3t_halo_list_create)
+  std::vector<int> list_len;
   // host state
   std::vector<int> ksplt, cpy;
   std::vector<T> cmax_h;
@@ -246,6 +250,9 @@ template <class T> struct Impl {
   int substep(int it, int hord, T lim_fac);
   int prepare(int hord, bool allow5 = true);
   int apply_damping(int it, bool mf_scaled);
+  int halo_list_move(int it, int lt, int list, T* buf, bool scatter);
+  int halo_list_create(const int* offs, int count, int* list);
+  int halo_local_table(const int* dst, const int* src, int len);
   int fv_tp_2d_host(int nlev, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx, const T* yfx, const T* ra_x,
                     const T* ra_y, T lim_fac, const T* mfx, const T* mfy, const T* mass, int nord, T damp_c);
   int alloc5();
@@ -276,10 +283,17 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   if (nt < 1 || nt > 6) return fail("fv3tracer: ntiles = %d outside 1..6", nt);
   if (nqmax < 1) return fail("fv3tracer: nq_max must be >= 1");
   for (int t = 0; t < 6; ++t) local_of[t] = -1;
+  sub_L = dims->sub_layout >= 2 ? dims->sub_layout : 0;
   for (int s = 0; s < nt; ++s) {
     const int gt = dims->tile_id[s] - 1;
-    if (gt < 0 || gt > 5 || local_of[gt] >= 0) return fail("fv3tracer: bad tile_id[%d] = %d", s, dims->tile_id[s]);
+    if (gt < 0 || gt > 5 || (!sub_L && local_of[gt] >= 0)) return fail("fv3tracer: bad tile_id[%d] = %d", s, dims->tile_id[s]);
     local_of[gt] = s;
+    if (sub_L) {  // which sides of the resident square lie on a tile edge, which of its corners are cube corners (A5Sub)
+      const int bi = dims->sub_bi[s], bj = dims->sub_bj[s];
+      if (bi < 0 || bi >= sub_L || bj < 0 || bj >= sub_L) return fail("fv3tracer: sub-domain (%d, %d) outside the %d x %d layout", bi, bj, sub_L, sub_L);
+      const bool w = bi == 0, e = bi == sub_L - 1, so = bj == 0, no = bj == sub_L - 1;
+      subflags[s] = fv3t::A5Sub{!w, !e, !so, !no, (w && so ? 1 : 0) | (e && so ? 2 : 0) | (e && no ? 4 : 0) | (w && no ? 8 : 0)};
+    }
   }
   CK(cudaSetDevice(dev));
   if (strm) {
@@ -327,7 +341,7 @@ template <class T> int Impl<T>::create(const fv3t_dims* dims, const T* const* g,
   // halo tables: local gathers (both tiles resident) + per-edge strips for remote exchange
   std::vector<int> hd, hs;
   const int nd = n + 6;
-  for (int s = 0; s < nt; ++s) {
+  for (int s = 0; s < nt && !sub_L; ++s) {  // (a sub-tile context gets its tables from the host: fv3t_halo_local_table, halo lists)
     const int gt = dims->tile_id[s] - 1;
     for (int e = 0; e < 4; ++e) {
       const EdgeMap& m = maps[gt][e];
@@ -380,6 +394,8 @@ template <class T> int Impl<T>::destroy() {
                   ksplt_d, par_d, cpy_d, kord_d, halo_dst, halo_src, row_buf, strip_buf, fld, fld_qs, del6_u, del6_v, dfx2, dfy2, dd2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int* l : lists)
+    if (l) cudaFree(l);
   for (int s = 0; s < 6; ++s)
     for (int e = 0; e < 4; ++e) {
       if (strip_idx[s][e]) cudaFree(strip_idx[s][e]);
@@ -481,11 +497,10 @@ template <class T> int Impl<T>::halo_local(int it) {
 
 template <class T>
 __global__ void k_strip(T* __restrict__ q, T* __restrict__ buf, const int* __restrict__ idx, int n, int npz, int nq,
-                        const int* __restrict__ ksplt, int it, int unpack) {
+                        const int* __restrict__ ksplt, int it, int unpack, int len) {
   const long plane = (long)(n + 6) * (n + 6);
   const int pl = blockIdx.y;  // iq*npz + kz
   if (it > ksplt[pl % npz]) return;
-  const int len = 3 * n;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < len; e += gridDim.x * blockDim.x) {
     if (unpack)
       q[(long)pl * plane + idx[e]] = buf[(long)pl * len + e];
@@ -496,12 +511,68 @@ __global__ void k_strip(T* __restrict__ q, T* __restrict__ buf, const int* __res
 
 template <class T> int Impl<T>::halo_pack(int it, int lt, int edge, T* buf, bool unpack) {
   if (lt < 0 || lt >= nt || edge < 0 || edge > 3) return fail("fv3tracer: bad tile/edge %d/%d", lt, edge);
+  if (sub_L) return fail("fv3tracer: the edge-strip exchange is for whole-tile contexts; sub-tile contexts use the halo lists");
   CK(cudaSetDevice(device));
   dim3 grid((3 * n + 255) / 256, nq_cur * npz);
   T* qt = q[(cur + it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
   kbegin();
   k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, unpack ? strip_halo[lt][edge] : strip_idx[lt][edge], n, npz, nq_cur, ksplt_d, it,
-                                       unpack ? 1 : 0);
+                                       unpack ? 1 : 0, 3 * n);
+  kend(KC_HALO);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class T> int Impl<T>::halo_list_create(const int* offs, int count, int* list) {
+  if (!list || count < 0 || (count > 0 && !offs)) return fail("fv3tracer: halo_list_create: bad arguments");
+  const int pl = (int)plane();
+  for (int e = 0; e < count; ++e)
+    if (offs[e] < 0 || offs[e] >= pl) return fail("fv3tracer: halo_list_create: offset %d outside the plane (%d cells)", offs[e], pl);
+  CK(cudaSetDevice(device));
+  int* d = nullptr;
+  if (count) {
+    CK(cudaMalloc((void**)&d, (size_t)count * sizeof(int)));
+    CK(cudaMemcpy(d, offs, (size_t)count * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  lists.push_back(d);
+  list_len.push_back(count);
+  *list = (int)lists.size() - 1;
+  return 0;
+}
+
+template <class T> int Impl<T>::halo_local_table(const int* dst, const int* src, int len) {
+  if (len < 0 || (len > 0 && (!dst || !src))) return fail("fv3tracer: halo_local_table: bad arguments");
+  const long total = (long)plane() * nt;
+  for (int e = 0; e < len; ++e)
+    if (dst[e] < 0 || dst[e] >= total || src[e] < 0 || src[e] >= total) return fail("fv3tracer: halo_local_table: offset outside the resident planes");
+  CK(cudaSetDevice(device));
+  CK(cudaStreamSynchronize(stream));
+  if (halo_dst) cudaFree(halo_dst);
+  if (halo_src) cudaFree(halo_src);
+  halo_dst = halo_src = nullptr;
+  halo_len = len;
+  if (len) {
+    CK(cudaMalloc((void**)&halo_dst, (size_t)len * sizeof(int)));
+    CK(cudaMalloc((void**)&halo_src, (size_t)len * sizeof(int)));
+    CK(cudaMemcpy(halo_dst, dst, (size_t)len * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(halo_src, src, (size_t)len * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+// generic gather (scatter) of the cells named by a registered list, every plane of the resident tracers of one resident tile
+template <class T> int Impl<T>::halo_list_move(int it, int lt, int list, T* buf, bool scatter) {
+  if (lt < 0 || lt >= nt) return fail("fv3tracer: bad local tile %d", lt);
+  if (list < 0 || list >= (int)lists.size()) return fail("fv3tracer: unknown halo list %d", list);
+  if (!buf) return fail("fv3tracer: halo_gather / halo_scatter: null buffer");
+  if (nq_cur < 1) return fail("fv3tracer: no resident tracers");
+  const int len = list_len[list];
+  if (len == 0) return 0;
+  CK(cudaSetDevice(device));
+  dim3 grid((len + 255) / 256, nq_cur * npz);
+  T* qt = q[(cur + it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
+  kbegin();
+  k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, lists[list], n, npz, nq_cur, ksplt_d, it, scatter ? 1 : 0, len);
   kend(KC_HALO);
   CK(cudaGetLastError());
   return 0;
@@ -586,7 +657,9 @@ template <class T> int Impl<T>::prepare(int hord, bool allow5) {
   // k_advect5 shares the staged level fields among the tracers of a CTA and takes one CTA per SM: with fewer than four resident
   // tracers (small tracer groups of a sharded run) the per-tracer CTAs of k_advect4 / k_advect2 keep more warps in flight.
   // Schemes outside fast_hord_ok run its exact-arithmetic instantiation (FV3T_STRICT=1 keeps everything on k_advect2).
-  call5 = fast && use5 && allow5 && fv3t::adv5_hord_ok(hord) && nq_cur >= 4;
+  call5 = fast && use5 && allow5 && fv3t::adv5_hord_ok(hord) && (nq_cur >= 4 || sub_L);
+  if (sub_L && !call5)
+    return fail("fv3tracer: sub-tile contexts run k_advect5 only (not with FV3T_STRICT=1 / FV3T_ADV5=0, not through tracer_step)");
   exact5 = call5 && !call_fast;
   auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
   if (call5) {
@@ -669,6 +742,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     p.iq0 = 0;
     p.nql = nq_cur;
     p.lim_fac = lim_fac;
+    for (int t = 0; t < nt; ++t) p.sub[t] = subflags[t];
     if (coef_wanted && it == 1 && !prof) {
       const int rcs = launch_coef_side();
       if (rcs) return rcs;
@@ -777,6 +851,7 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
 // to the field the advection kernel has just written; see fv3t_deln.cuh.
 template <class T> int Impl<T>::apply_damping(int it, bool mf_scaled) {
   if (it != 1 || !(damp_trdm > T(1.e-4))) return 0;
+  if (sub_L) return fail("fv3tracer: tracer damping is not available in sub-tile contexts");
   if (!del6_u) return fail("fv3tracer: tracer damping needs the damping metrics (fv3t_*_set_damping)");
   if (nt != 6) return fail("fv3tracer: tracer damping needs all six tiles resident (the dp1 halo is filled locally)");
   if (damp_nord < 0 || damp_nord > 2) return fail("fv3tracer: nord_tr = %d outside 0..2 (deln_flux needs nord + 1 <= ng halo cells)", damp_nord);
@@ -843,6 +918,7 @@ int Impl<T>::fv_tp_2d_host(int nlev, T* q, const T* crx, const T* cry, int hord,
                            T damp_c) {
   if (!((hord >= 1 && hord <= 13) || hord == -5)) return fail("fv3tracer: hord = %d is not a scheme of xppm/yppm", hord);
   if (nlev < 1) return fail("fv3tracer: fv_tp_2d: nlev = %d", nlev);
+  if (sub_L) return fail("fv3tracer: fv_tp_2d: not available in sub-tile contexts");
   if (!q || !crx || !cry || !fx || !fy || !xfx || !yfx || !ra_x || !ra_y) return fail("fv3tracer: fv_tp_2d: null array");
   if ((mfx_h == nullptr) != (mfy_h == nullptr)) return fail("fv3tracer: fv_tp_2d: mfx and mfy must be given together (tp_core.F90:209)");
   const bool tracer = mfx_h != nullptr;
@@ -976,7 +1052,7 @@ template <class T> int Impl<T>::finish() {
 }
 
 template <class T> int Impl<T>::tracer_2d_resident(int nq, int hord, int q_split, T lim_fac, int* nsplt_out) {
-  if (nt != 6) return fail("fv3tracer: tracer_2d needs all six tiles resident (ntiles = %d); use the *_begin/halo/substep calls", nt);
+  if (nt != 6 || sub_L) return fail("fv3tracer: tracer_2d needs all six whole tiles resident (ntiles = %d); use the *_begin/halo/substep calls", nt);
   std::vector<T> cm(npz);
   int rc = begin(nq, q_split, cm.data());
   if (rc) return rc;
@@ -1137,6 +1213,7 @@ template <class T> int Impl<T>::remap_alloc() {
 template <class T>
 int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const T* hpe, const T* hak, const T* hbk, T hptop,
                          T* hdelp, int nq, int hord, int q_split, T lim_fac, const int* kord, int fill, int* nsplt_out) {
+  if (sub_L) return fail("fv3tracer: tracer_step is for whole-tile contexts");
   if (nt != 6) return fail("fv3tracer: tracer_step needs all six tiles resident (ntiles = %d)", nt);
   if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
   CK(cudaSetDevice(device));
@@ -1596,6 +1673,14 @@ extern "C" int fv3t_device_count(void) {
     CK(cudaStreamSynchronize(I->stream));                                                                                      \
     return 0;                                                                                                                  \
   }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_gather(fv3t_ctx* ctx, int it, int local_tile, int list, REAL* dev_buf) {                     \
+    NEED(ctx, P);                                                                                                              \
+    return I->halo_list_move(it, local_tile, list, dev_buf, false);                                                            \
+  }                                                                                                                            \
+  extern "C" int fv3t_##P##_halo_scatter(fv3t_ctx* ctx, int it, int local_tile, int list, const REAL* dev_buf) {              \
+    NEED(ctx, P);                                                                                                              \
+    return I->halo_list_move(it, local_tile, list, const_cast<REAL*>(dev_buf), true);                                          \
+  }                                                                                                                            \
   extern "C" int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac) {                                 \
     NEED(ctx, P);                                                                                                              \
     return I->substep(it, hord, lim_fac);                                                                                      \
@@ -1636,6 +1721,19 @@ extern "C" void* fv3t_device_ptr(fv3t_ctx* ctx, int field) {
 extern "C" size_t fv3t_halo_strip_elems(fv3t_ctx* ctx) {
   if (!ctx) return 0;
   return DISPATCH(ctx, (size_t)3 * ctx->f64->n * ctx->f64->npz * ctx->f64->nq_cur, (size_t)3 * ctx->f32->n * ctx->f32->npz * ctx->f32->nq_cur);
+}
+extern "C" int fv3t_halo_list_create(fv3t_ctx* ctx, const int* offsets, int count, int* list) {
+  if (!ctx) return fail("fv3tracer: null context");
+  return DISPATCH(ctx, ctx->f64->halo_list_create(offsets, count, list), ctx->f32->halo_list_create(offsets, count, list));
+}
+extern "C" int fv3t_halo_list_count(fv3t_ctx* ctx, int list) {
+  if (!ctx) return -1;
+  const std::vector<int>& ll = DISPATCH(ctx, ctx->f64->list_len, ctx->f32->list_len);
+  return (list >= 0 && list < (int)ll.size()) ? ll[list] : -1;
+}
+extern "C" int fv3t_halo_local_table(fv3t_ctx* ctx, const int* dst, const int* src, int len) {
+  if (!ctx) return fail("fv3tracer: null context");
+  return DISPATCH(ctx, ctx->f64->halo_local_table(dst, src, len), ctx->f32->halo_local_table(dst, src, len));
 }
 extern "C" int fv3t_neighbor(fv3t_ctx* ctx, int global_tile, int edge, int* nbr_tile, int* nbr_edge, int* rotated) {
   if (!ctx || global_tile < 1 || global_tile > 6 || edge < 0 || edge > 3) return fail("fv3tracer: bad tile/edge");

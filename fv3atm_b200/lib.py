@@ -15,15 +15,16 @@ KCLASS = {"advect": 0, "remap": 1, "halo": 2, "cmax": 3, "scale": 4}
 # every symbol include/fv3tracer.h declares
 _PER_PREC = ["create", "tracer_2d", "tracer_2d_1L", "set_damping", "remap_tracers", "tracer_step", "mapn_tracer", "map_scalar", "map1_ppm", "map_field", "fv_tp_2d", "upload", "download", "set_vertical",
              "tracer_2d_resident", "remap_tracers_resident", "remap_prepare", "tracer_2d_begin", "tracer_2d_set_cmax", "halo_local",
-             "halo_pack", "halo_unpack", "halo_pack_host", "halo_unpack_host", "tracer_2d_substep", "tracer_2d_finish"]
+             "halo_pack", "halo_unpack", "halo_pack_host", "halo_unpack_host", "halo_gather", "halo_scatter", "tracer_2d_substep", "tracer_2d_finish"]
 _COMMON = ["fv3t_last_error", "fv3t_device_count", "fv3t_destroy", "fv3t_sync", "fv3t_device_ptr", "fv3t_halo_strip_elems",
-           "fv3t_neighbor", "fv3t_kernel_launches", "fv3t_timer_start", "fv3t_timer_stop_ms", "fv3t_profile_enable",
+           "fv3t_neighbor", "fv3t_halo_list_create", "fv3t_halo_list_count", "fv3t_halo_local_table", "fv3t_kernel_launches", "fv3t_timer_start", "fv3t_timer_stop_ms", "fv3t_profile_enable",
            "fv3t_profile_get_ms"]
 EXPORTS = _COMMON + [f"fv3t_{p}_{f}" for p in ("f64", "f32") for f in _PER_PREC]
 
 
 class Dims(C.Structure):
-    _fields_ = [("npx", C.c_int), ("npz", C.c_int), ("nq_max", C.c_int), ("ntiles", C.c_int), ("tile_id", C.c_int * 6)]
+    _fields_ = [("npx", C.c_int), ("npz", C.c_int), ("nq_max", C.c_int), ("ntiles", C.c_int), ("tile_id", C.c_int * 6),
+                ("sub_layout", C.c_int), ("sub_bi", C.c_int * 6), ("sub_bj", C.c_int * 6)]
 
 
 class GridPtrs(C.Structure):

@@ -147,3 +147,195 @@ class SubMosaic:
         flat = stack.reshape(stack.shape[0], -1, md * md)
         flat[ds, :, do] = flat[ss, :, so]
         return stack
+
+
+# ---- distribution over ranks and contexts ------------------------------------------------------------------------------------
+def assign(nsub: int, world: int, max_per_ctx: int = 6):
+    """owner[s] = (rank, context index on that rank, local tile in that context): contiguous blocks of sub-domains per rank (so that
+    the sub-domains of a face stay together), split into contexts of at most six resident sub-domains (fv3t_dims.tile_id[6])."""
+    if nsub % world:
+        raise ValueError(f"{nsub} sub-domains do not divide over {world} ranks")
+    per = nsub // world
+    owner = []
+    for s in range(nsub):
+        r, k = divmod(s, per)
+        owner.append((r, k // max_per_ctx, k % max_per_ctx))
+    return owner
+
+
+class ExchangePlan:
+    """The halo update of a sub-domain mosaic from the point of view of one rank, in three classes:
+      local[c]   = (dst_flat, src_flat): both sub-domains resident in context c -> fv3t_halo_local_table / fv3t_*_halo_local
+      copies     = [(src_ctx, src_lt, src_offs, dst_ctx, dst_lt, dst_offs)]: same rank, different contexts
+      sends[p] / recvs[p] = [(ctx, lt, offs)] in one global order (sorted by (dst sub, src sub)): one message per peer rank p,
+                   the pieces concatenated, each piece `planes x len(offs)` values."""
+
+    def __init__(self, mo: SubMosaic, owner, rank: int):
+        self.rank = rank
+        md = mo.m + 2 * NG
+        plane = md * md
+        self.local, self.copies, self.sends, self.recvs = {}, [], {}, {}
+        loc = {}
+        for (d, s), (doff, soff) in sorted(mo.pair_lists().items()):
+            rd, cd, ld = owner[d]
+            rs, cs_, ls = owner[s]
+            if rd == rank and rs == rank:
+                if cd == cs_:
+                    a = loc.setdefault(cd, ([], []))
+                    a[0].append(doff.astype(np.int64) + ld * plane)
+                    a[1].append(soff.astype(np.int64) + ls * plane)
+                else:
+                    self.copies.append((cs_, ls, soff, cd, ld, doff))
+            elif rs == rank:
+                self.sends.setdefault(rd, []).append((cs_, ls, soff))
+            elif rd == rank:
+                self.recvs.setdefault(rs, []).append((cd, ld, doff))
+        for c, (a, b) in loc.items():
+            self.local[c] = (np.concatenate(a).astype(np.int32), np.concatenate(b).astype(np.int32))
+
+    def message_cells(self, peer: int, sending: bool) -> int:
+        return sum(len(o) for _, _, o in (self.sends if sending else self.recvs).get(peer, []))
+
+
+class SubMosaicStep:
+    """tracer_2d + tracer remap of ONE global problem decomposed into L x L sub-domains per tile, this rank's share resident in
+    one or more sub-tile contexts (fv3t_dims.sub_layout).  The two collective sites of the reference are explicit: the
+    mp_reduce_max of cmax (fv_tracer2d.F90:433) and the q halo update per sub-step (:499) -- here gather lists that also carry
+    the diagonal blocks, like mpp_update_domains does for a rank that owns part of a tile."""
+
+    def __init__(self, mo: SubMosaic, rank: int, world: int, device: int, npz: int, nq: int, dtype, metrics: dict, group=None):
+        import torch
+        from .tracer import TracerContext
+        self.torch = torch
+        self.mo, self.rank, self.world, self.group = mo, rank, world, group
+        self.npz, self.nq = npz, nq
+        self.dev = torch.device(f"cuda:{device}")
+        self.tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.owner = assign(len(mo), world)
+        self.mine = [s for s in range(len(mo)) if self.owner[s][0] == rank]
+        nctx = 1 + max(self.owner[s][1] for s in self.mine)
+        self.ctx_subs = [[s for s in self.mine if self.owner[s][1] == c] for c in range(nctx)]
+        # ONE stream for every context of the rank and for the collectives: the cross-context copies and the packed messages are
+        # ordered by the stream alone (a context without a stream handle creates a private one)
+        self.stream = torch.cuda.Stream(self.dev)
+        stream = self.stream.cuda_stream
+        self.ctxs = []
+        for subs in self.ctx_subs:
+            g = {k: np.stack([mo.metrics(metrics, s)[k] for s in subs]) for k in ("area", "rarea", "dx", "dy", "dxa", "dya", "sin_sg")}
+            self.ctxs.append(TracerContext(mo.m + 1, npz, nq, g, dtype=dtype, tiles=[mo.subs[s].tile + 1 for s in subs], device=device,
+                                           stream=stream, sub_layout=mo.L, sub_blocks=[(mo.subs[s].bi, mo.subs[s].bj) for s in subs]))
+        self.plan = ExchangePlan(mo, self.owner, rank)
+        for c, (dst, src) in self.plan.local.items():
+            self.ctxs[c].halo_local_table(dst, src)
+        planes = npz * nq
+        mk = lambda ne: torch.empty(max(ne, 1), dtype=self.tdt, device=self.dev)
+        self._lists = {}
+        self.copy_buf = mk(planes * max([len(o) for _, _, o, _, _, _ in self.plan.copies] + [0]))
+        self.sbuf = {p: mk(planes * self.plan.message_cells(p, True)) for p in self.plan.sends}
+        self.rbuf = {p: mk(planes * self.plan.message_cells(p, False)) for p in self.plan.recvs}
+        self.cmax_dev = torch.empty(npz, dtype=self.tdt, device=self.dev)
+        self.halo_bytes = sum(b.numel() for b in self.sbuf.values()) * self.cmax_dev.element_size()
+
+    def _list(self, c, offs):
+        key = (c, offs.ctypes.data)
+        if key not in self._lists:
+            self._lists[key] = (self.ctxs[c].halo_list_create(offs), offs)  # keep offs alive: its address is the key
+        return self._lists[key][0]
+
+    def upload(self, field: str, whole: np.ndarray, cut):
+        """whole-tile array -> the resident sub-domain slices (cut = the SubMosaic slicer of that field)"""
+        for c, subs in enumerate(self.ctx_subs):
+            a = np.ascontiguousarray(np.stack([cut(whole, s) for s in subs]))
+            self.ctxs[c].upload(field, a, nq=self.nq if field == "q" else None)
+
+    def upload_case(self, case):
+        mo = self.mo
+        self.upload("q", case.q, mo.cells)
+        self.upload("dp1", case.dp1, mo.cells)
+        self.upload("cx", case.cx, mo.xface)
+        self.upload("cy", case.cy, mo.yface)
+        self.upload("mfx", case.mfx, mo.mfx)
+        self.upload("mfy", case.mfy, mo.mfy)
+        self.upload("pe", case.pe, mo.pe)
+        for ctx in self.ctxs:
+            ctx.set_vertical(case.ak, case.bk, case.ptop)
+
+    def download(self, field: str, whole: np.ndarray):
+        """interiors of the resident sub-domains -> the whole-tile array (tile axis first)"""
+        md = self.mo.m + 2 * NG
+        for c, subs in enumerate(self.ctx_subs):
+            shape = (len(subs),) + whole.shape[1:-2] + (md, md)
+            a = np.zeros(shape, dtype=whole.dtype)
+            self.ctxs[c].download(field, a, nq=self.nq if field == "q" else None)
+            for k, s in enumerate(subs):
+                self.mo.put_interior(whole, s, a[k])
+        return whole
+
+    def exchange(self, it: int):
+        with self.torch.cuda.stream(self.stream):
+            self._exchange(it)
+
+    def _exchange(self, it: int):
+        torch = self.torch
+        planes = self.npz * self.nq
+        esz = self.cmax_dev.element_size()
+        for ctx in self.ctxs:
+            ctx.halo_local(it)
+        for (cs_, ls, soff, cd, ld, doff) in self.plan.copies:
+            self.ctxs[cs_].halo_gather(it, ls, self._list(cs_, soff), self.copy_buf.data_ptr())
+            self.ctxs[cd].halo_scatter(it, ld, self._list(cd, doff), self.copy_buf.data_ptr())
+        if not self.plan.sends and not self.plan.recvs:
+            return
+        import torch.distributed as dist
+        for p, pieces in self.plan.sends.items():
+            at = 0
+            for (c, lt, offs) in pieces:
+                self.ctxs[c].halo_gather(it, lt, self._list(c, offs), self.sbuf[p].data_ptr() + at * esz)
+                at += planes * len(offs)
+        ops = []
+        for p in sorted(set(self.plan.sends) | set(self.plan.recvs)):
+            # lower rank sends first: both ends of a pair enqueue in one order
+            first_send = self.rank < p
+            for kind in ((0, 1) if first_send else (1, 0)):
+                if kind == 0 and p in self.sbuf:
+                    ops.append(dist.P2POp(dist.isend, self.sbuf[p], p, group=self.group))
+                if kind == 1 and p in self.rbuf:
+                    ops.append(dist.P2POp(dist.irecv, self.rbuf[p], p, group=self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for p, pieces in self.plan.recvs.items():
+            at = 0
+            for (c, lt, offs) in pieces:
+                self.ctxs[c].halo_scatter(it, lt, self._list(c, offs), self.rbuf[p].data_ptr() + at * esz)
+                at += planes * len(offs)
+
+    def tracer_2d(self, hord: int, q_split: int = 0, lim_fac: float = 1.0) -> int:
+        torch = self.torch
+        cm = None
+        for ctx in self.ctxs:
+            c = ctx.tracer_2d_begin(self.nq, q_split)
+            cm = c if cm is None else np.maximum(cm, c)
+        if self.world > 1 and q_split == 0:
+            import torch.distributed as dist
+            with torch.cuda.stream(self.stream):
+                self.cmax_dev.copy_(torch.from_numpy(np.ascontiguousarray(cm)))
+                dist.all_reduce(self.cmax_dev, op=dist.ReduceOp.MAX, group=self.group)
+                cm = self.cmax_dev.cpu().numpy()
+        nsplt = 0
+        for ctx in self.ctxs:
+            nsplt = ctx.tracer_2d_set_cmax(cm, q_split)
+        for it in range(1, nsplt + 1):
+            self.exchange(it)
+            for ctx in self.ctxs:
+                ctx.tracer_2d_substep(it, hord, lim_fac)
+        for ctx in self.ctxs:
+            ctx.tracer_2d_finish()
+        return nsplt
+
+    def remap(self, kord, fill=True):
+        for ctx in self.ctxs:
+            ctx.remap_tracers_resident(self.nq, kord, fill)
+
+    def close(self):
+        for ctx in self.ctxs:
+            ctx.close()

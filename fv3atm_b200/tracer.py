@@ -17,18 +17,27 @@ class TracerContext:
     """Device-resident state of the path for `ntiles` cubed-sphere tiles on one GPU (fv3t_ctx)."""
 
     def __init__(self, npx: int, npz: int, nq_max: int, grid: dict, dtype=np.float64, tiles=(1, 2, 3, 4, 5, 6),
-                 device: int = 0, stream: int | None = None):
+                 device: int = 0, stream: int | None = None, sub_layout: int = 0, sub_blocks=None):
+        """sub_layout = L >= 2: a sub-tile context (fv3t_dims.sub_layout): `tiles` names the tile of every resident sub-domain,
+        sub_blocks its (bi, bj) block in the L x L decomposition, npx is the LOCAL extent + 1 and `grid` holds the local metric
+        arrays, one leading entry per resident sub-domain."""
         self.dtype = np.dtype(dtype)
         self.npx, self.npz, self.nq_max = int(npx), int(npz), int(nq_max)
         self.n = self.npx - 1
         self.tiles = tuple(int(t) for t in tiles)
         self.nt = len(self.tiles)
-        d = L.Dims(self.npx, self.npz, self.nq_max, self.nt, (C.c_int * 6)(*(list(self.tiles) + [0] * (6 - self.nt))))
+        self.sub_layout = int(sub_layout)
+        pad = lambda v: (C.c_int * 6)(*(list(v) + [0] * (6 - len(v))))
+        blocks = list(sub_blocks) if sub_blocks is not None else []
+        if self.sub_layout >= 2 and len(blocks) != self.nt:
+            raise ValueError("sub_blocks: one (bi, bj) per resident sub-domain")
+        d = L.Dims(self.npx, self.npz, self.nq_max, self.nt, pad(self.tiles), self.sub_layout, pad([b[0] for b in blocks]),
+                   pad([b[1] for b in blocks]))
         g = L.GridPtrs()
         self._keep = []
         for k in ("area", "rarea", "dx", "dy", "dxa", "dya", "sin_sg"):
             a = np.ascontiguousarray(grid[k], dtype=self.dtype)
-            if a.shape[0] != self.nt:
+            if a.shape[0] != self.nt and self.sub_layout < 2:
                 a = np.ascontiguousarray(a[[t - 1 for t in self.tiles]])
             self._keep.append(a)
             setattr(g, k, a.ctypes.data)
@@ -198,6 +207,25 @@ class TracerContext:
 
     def halo_unpack(self, it, local_tile, edge, dev_ptr):
         L.check(self._f("halo_unpack")(self._h, int(it), int(local_tile), int(edge), C.c_void_p(dev_ptr)))
+
+    # generic exchange by gather list (sub-tile contexts)
+    def halo_list_create(self, offsets) -> int:
+        offs = np.ascontiguousarray(offsets, dtype=np.int32)
+        lid = C.c_int(-1)
+        L.check(L.load().fv3t_halo_list_create(self._h, L.ptr(offs), int(offs.size), C.byref(lid)))
+        return lid.value
+
+    def halo_local_table(self, dst, src):
+        dst = np.ascontiguousarray(dst, dtype=np.int32)
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        assert dst.size == src.size
+        L.check(L.load().fv3t_halo_local_table(self._h, L.ptr(dst), L.ptr(src), int(dst.size)))
+
+    def halo_gather(self, it, local_tile, list_id, dev_ptr):
+        L.check(self._f("halo_gather")(self._h, int(it), int(local_tile), int(list_id), C.c_void_p(dev_ptr)))
+
+    def halo_scatter(self, it, local_tile, list_id, dev_ptr):
+        L.check(self._f("halo_scatter")(self._h, int(it), int(local_tile), int(list_id), C.c_void_p(dev_ptr)))
 
     def tracer_2d_substep(self, it, hord, lim_fac=1.0):
         L.check(self._f("tracer_2d_substep")(self._h, int(it), int(hord), self._ct(lim_fac)))

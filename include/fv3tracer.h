@@ -44,6 +44,16 @@ typedef struct fv3t_dims {
   int nq_max;     /* capacity: largest nq any call will pass                                     */
   int ntiles;     /* tiles resident in this context, 1..6                                        */
   int tile_id[6]; /* global tile numbers (1..6) of the resident tiles, in storage order          */
+  /* Sub-tile contexts -- a rank that owns PART of a tile (bd%is..ie a proper sub-range of 1..npx-1, layout > 1,1;
+     fv_arrays.F90:1178-1186).  sub_layout = 0 or 1: whole tiles.  sub_layout = L >= 2: every resident "tile" t is the square
+     sub-domain (sub_bi[t], sub_bj[t]) (0-based block column / row) of the L x L decomposition of tile tile_id[t]; npx is then
+     the LOCAL extent + 1 (global npx = L * (npx - 1) + 1), all array shapes are the local ones, and the same tile may appear
+     several times.  The tile-edge formulas of xppm / yppm are applied on the sides that lie on a tile edge only and
+     copy_corners' views at true cube corners only (gridstruct%sw_corner .., fv_arrays.F90:181); every other halo cell --
+     the diagonal blocks included -- must be delivered by the halo exchange (fv3t_halo_list_create, fv3t_*_halo_gather /
+     _scatter, fv3t_halo_local_table).  Sub-tile contexts are driven through the tracer_2d building blocks and the remap. */
+  int sub_layout;
+  int sub_bi[6], sub_bj[6];
 } fv3t_dims;
 
 /* Device-resident fields addressable through fv3t_*_upload/download/device_ptr */
@@ -182,6 +192,12 @@ int fv3t_device_count(void);
      the device, copied out, exchanged by the host (mpp_send / mpp_recv in the Fortran shim), copied in and scattered */        \
   int fv3t_##P##_halo_pack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* host_buf);                        \
   int fv3t_##P##_halo_unpack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* host_buf);                \
+  /* Generic halo exchange by gather list (sub-tile contexts; works for whole tiles too): `list` names a set of plane offsets    \
+     (row-major (j+2)*(npx+5) + (i+2)) registered with fv3t_halo_list_create.  gather: dev_buf[pl*count + e] = q_in(it)[tile     \
+     local_tile][plane pl][offset e] for the planes pl = iq*npz + k of the resident tracers; scatter is the inverse.  Levels    \
+     whose ksplt(k) < it are skipped on both sides, like the strips above. */                                                  \
+  int fv3t_##P##_halo_gather(fv3t_ctx* ctx, int it, int local_tile, int list, REAL* dev_buf);                            \
+  int fv3t_##P##_halo_scatter(fv3t_ctx* ctx, int it, int local_tile, int list, const REAL* dev_buf);                     \
   int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac);                                      \
   int fv3t_##P##_tracer_2d_finish(fv3t_ctx* ctx);
 
@@ -189,6 +205,13 @@ FV3T_DECLARE(f64, double)
 FV3T_DECLARE(f32, float)
 
 /* Precision-independent calls */
+/* Registers `count` plane offsets (host array) as a gather / scatter list of this context; *list receives its handle. */
+int fv3t_halo_list_create(fv3t_ctx* ctx, const int* offsets, int count, int* list);
+int fv3t_halo_list_count(fv3t_ctx* ctx, int list);
+/* Replaces the table fv3t_*_halo_local applies (halo cells whose source is resident in the SAME context): len pairs of flat
+   offsets (local_tile * (npx+5) + j + 2) * (npx+5) + i + 2 into the stack of resident planes.  Whole-tile contexts build this
+   table themselves from the cubed-sphere contact table; a sub-tile context starts with an empty one. */
+int fv3t_halo_local_table(fv3t_ctx* ctx, const int* dst, const int* src, int len);
 int fv3t_destroy(fv3t_ctx* ctx);
 int fv3t_sync(fv3t_ctx* ctx);
 /* Base of the device mirror.  FV3T_Q: the buffer that CURRENTLY holds the tracers -- tracer_2d (odd nsplt) and the remap

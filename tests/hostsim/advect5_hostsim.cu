@@ -53,7 +53,7 @@ template <class T, int OI, int OO, bool EX> struct Sim {
   template <int PH, int PHQ, bool YE, bool XE, int PH4, int PH1>
   void step(const unsigned char* stage4, const unsigned char* stage, const unsigned char* stage1, int r, bool do4, bool do1) {
     for (int tid = 0; tid < A5_GW; ++tid) {
-      adv5_issue_q<T, OI, OO, PHQ, YE>(c, st[tid], th[tid], r + 2);
+      adv5_issue_q<T, OI, OO, PHQ, YE>(p, c, st[tid], th[tid], r + 2);
       adv5_phase2<T, OI, OO, PH, XE>(p, c, st[tid], th[tid], r);
       if (do4) adv5_phase4<T, OI, OO, PH4, YE, EX>(p, c, st[tid], th[tid], a5_view<T>(stage4, tid, c.i0 - 1), r - 1);
     }
@@ -90,8 +90,8 @@ template <class T, int OI, int OO, bool EX> static void run_substep(const Adv5Pa
         for (int tid = 0; tid < A5_GW; ++tid) {
           th[tid] = adv5_thread(c, tid);
           adv5_init<T, OI, OO>(p, c, th[tid], gs, st[tid]);
-          adv5_issue_q<T, OI, OO, 0, true>(c, st[tid], th[tid], -2);
-          adv5_issue_q<T, OI, OO, 1, true>(c, st[tid], th[tid], -1);
+          adv5_issue_q<T, OI, OO, 0, true>(p, c, st[tid], th[tid], -2);
+          adv5_issue_q<T, OI, OO, 1, true>(p, c, st[tid], th[tid], -1);
           adv5_phase1<T, OI, OO, 0, true, EX>(p, c, st[tid], th[tid], a5_view<T>(sg, tid, c.i0 - 1), -2);
         }
         for (int b = 0; b < nblocks; ++b) {
