@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--hord", type=int, default=8)
     ap.add_argument("--kord", type=int, default=9)
     ap.add_argument("--courant", type=float, default=0.7)
-    ap.add_argument("--shard", default="face", choices=["tracer", "face", "group"],
+    ap.add_argument("--sub-layout", type=int, default=2, help="--shard sub: L x L sub-domains per tile")
+    ap.add_argument("--shard", default="face", choices=["tracer", "face", "group", "sub"],
                     help="N > 1 ranks.  face (default) / group: ONE nq-tracer problem split by faces x tracer groups / by tracer groups only "
                          "(strong scaling, BASELINE config 4 / 5); tracer: every rank its own nq tracers (replicas, weak)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -294,6 +295,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.shard == "sub":
+        from fv3atm_b200 import subdomain
+        args.clock_sampler = ClockSampler
+        return subdomain.bench_submosaic(args, rank, world, local_rank)
     if args.shard in ("face", "group") and world > 1:
         from fv3atm_b200 import partition
         args.clock_sampler = ClockSampler

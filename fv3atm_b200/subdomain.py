@@ -197,6 +197,37 @@ class ExchangePlan:
         return sum(len(o) for _, _, o in (self.sends if sending else self.recvs).get(peer, []))
 
 
+def run_exchange(plan: ExchangePlan, planes: int, copy_buf, sbuf: dict, rbuf: dict, gather, scatter, group=None):
+    """The cross-context and cross-rank part of one halo update.  gather(ctx, local_tile, offsets, view) fills a flat buffer view
+    with `planes x len(offsets)` values, scatter is its inverse; the buffers are torch tensors (CUDA with NCCL, CPU with gloo)."""
+    for (cs_, ls, soff, cd, ld, doff) in plan.copies:
+        v = copy_buf[:planes * len(soff)]
+        gather(cs_, ls, soff, v)
+        scatter(cd, ld, doff, v)
+    if not plan.sends and not plan.recvs:
+        return
+    import torch.distributed as dist
+    for p, pieces in plan.sends.items():
+        at = 0
+        for (c, lt, offs) in pieces:
+            gather(c, lt, offs, sbuf[p][at:at + planes * len(offs)])
+            at += planes * len(offs)
+    ops = []
+    for p in sorted(set(plan.sends) | set(plan.recvs)):
+        for kind in ((0, 1) if plan.rank < p else (1, 0)):  # both ends of a pair enqueue in one order
+            if kind == 0 and p in sbuf:
+                ops.append(dist.P2POp(dist.isend, sbuf[p], p, group=group))
+            if kind == 1 and p in rbuf:
+                ops.append(dist.P2POp(dist.irecv, rbuf[p], p, group=group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for p, pieces in plan.recvs.items():
+        at = 0
+        for (c, lt, offs) in pieces:
+            scatter(c, lt, offs, rbuf[p][at:at + planes * len(offs)])
+            at += planes * len(offs)
+
+
 class SubMosaicStep:
     """tracer_2d + tracer remap of ONE global problem decomposed into L x L sub-domains per tile, this rank's share resident in
     one or more sub-tile contexts (fv3t_dims.sub_layout).  The two collective sites of the reference are explicit: the
@@ -276,38 +307,11 @@ class SubMosaicStep:
             self._exchange(it)
 
     def _exchange(self, it: int):
-        torch = self.torch
-        planes = self.npz * self.nq
-        esz = self.cmax_dev.element_size()
         for ctx in self.ctxs:
             ctx.halo_local(it)
-        for (cs_, ls, soff, cd, ld, doff) in self.plan.copies:
-            self.ctxs[cs_].halo_gather(it, ls, self._list(cs_, soff), self.copy_buf.data_ptr())
-            self.ctxs[cd].halo_scatter(it, ld, self._list(cd, doff), self.copy_buf.data_ptr())
-        if not self.plan.sends and not self.plan.recvs:
-            return
-        import torch.distributed as dist
-        for p, pieces in self.plan.sends.items():
-            at = 0
-            for (c, lt, offs) in pieces:
-                self.ctxs[c].halo_gather(it, lt, self._list(c, offs), self.sbuf[p].data_ptr() + at * esz)
-                at += planes * len(offs)
-        ops = []
-        for p in sorted(set(self.plan.sends) | set(self.plan.recvs)):
-            # lower rank sends first: both ends of a pair enqueue in one order
-            first_send = self.rank < p
-            for kind in ((0, 1) if first_send else (1, 0)):
-                if kind == 0 and p in self.sbuf:
-                    ops.append(dist.P2POp(dist.isend, self.sbuf[p], p, group=self.group))
-                if kind == 1 and p in self.rbuf:
-                    ops.append(dist.P2POp(dist.irecv, self.rbuf[p], p, group=self.group))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        for p, pieces in self.plan.recvs.items():
-            at = 0
-            for (c, lt, offs) in pieces:
-                self.ctxs[c].halo_scatter(it, lt, self._list(c, offs), self.rbuf[p].data_ptr() + at * esz)
-                at += planes * len(offs)
+        gather = lambda c, lt, offs, view: self.ctxs[c].halo_gather(it, lt, self._list(c, offs), view.data_ptr())
+        scatter = lambda c, lt, offs, view: self.ctxs[c].halo_scatter(it, lt, self._list(c, offs), view.data_ptr())
+        run_exchange(self.plan, self.npz * self.nq, self.copy_buf, self.sbuf, self.rbuf, gather, scatter, self.group)
 
     def tracer_2d(self, hord: int, q_split: int = 0, lim_fac: float = 1.0) -> int:
         torch = self.torch
@@ -339,3 +343,176 @@ class SubMosaicStep:
     def close(self):
         for ctx in self.ctxs:
             ctx.close()
+
+
+# ---- bench.py --shard sub ---------------------------------------------------------------------------------------------------------
+def fill_submosaic(run: SubMosaicStep, grid, args, device: int):
+    """Synthetic inputs of the resident sub-domains, generated on the device: each tile this rank touches is generated once in a
+    temporary whole-tile context (the generator of bench.py's single-GPU workload) and its windows are copied into the sub-tile
+    contexts."""
+    import torch
+    from . import synthetic_device as sd
+    from .devarray import field_view
+    from .tracer import TracerContext
+    mo, n, m = run.mo, run.mo.n, run.mo.m
+    win = {"q": (6, 6), "dp1": (6, 6), "cx": (6, 1), "cy": (1, 6), "mfx": (0, 1), "mfy": (1, 0)}
+    ak = bk = ptop = None
+    with torch.cuda.stream(run.stream):
+        for tile in sorted({mo.subs[s].tile for s in run.mine}):
+            w = TracerContext(n + 1, run.npz, run.nq, grid.astype(args.dtype), dtype=args.dtype, tiles=[tile + 1], device=device,
+                              stream=run.stream.cuda_stream)
+            ak, bk, ptop = sd.fill_context(w, grid, run.nq, courant=args.courant, seed=20260101, device=device)
+            for c, subs in enumerate(run.ctx_subs):
+                for lt, s in enumerate(subs):
+                    sb = mo.subs[s]
+                    if sb.tile != tile:
+                        continue
+                    for f, (re, ce) in win.items():
+                        nq = run.nq if f == "q" else None
+                        field_view(run.ctxs[c], f, nq, device)[lt].copy_(
+                            field_view(w, f, nq, device)[0][..., sb.j0:sb.j0 + m + re, sb.i0:sb.i0 + m + ce])
+                    field_view(run.ctxs[c], "pe", None, device)[lt].copy_(
+                        field_view(w, "pe", None, device)[0][sb.j0:sb.j0 + m + 2, :, sb.i0:sb.i0 + m + 2])
+            run.stream.synchronize()
+            w.close()
+        for ctx in run.ctxs:
+            ctx.set_vertical(ak, bk, ptop)
+    return ak, bk, ptop
+
+
+def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
+    """bench.py --shard sub: ONE global problem decomposed into L x L sub-domains per tile (24 for L = 2: SURVEY.md section 8e), the
+    sub-domains of a rank resident in sub-tile contexts; per sub-step one packed NCCL message per peer pair (side halos and diagonal
+    blocks), per call one all-reduce(max) of cmax; kernels, packing and collectives ordered on one CUDA stream per rank."""
+    import json
+    import os
+    import time
+    import torch
+    import torch.distributed as dist
+
+    n, npz, nq, L = args.n, args.npz, args.nq, args.sub_layout
+    dev = torch.device(f"cuda:{local_rank}")
+    grid = cs.make_grid(n)
+    w = 8 if args.dtype == "float64" else 4
+    mo = SubMosaic(n, L)
+    run = SubMosaicStep(mo, rank, world, local_rank, npz, nq, args.dtype, grid.astype(args.dtype))
+    ak, bk, ptop = fill_submosaic(run, grid, args, local_rank)
+    kord = np.full(nq, args.kord, dtype=np.int32)
+
+    def one():
+        ns = run.tracer_2d(args.hord)
+        run.remap(kord, fill=True)
+        return ns
+
+    def barrier():
+        run.stream.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    nsplt = 1
+    for _ in range(max(args.warmup, 3)):
+        nsplt = one()
+    barrier()
+    sampler = None
+    if rank == 0 and getattr(args, "clock_sampler", None):
+        sampler = args.clock_sampler(local_rank)
+        sampler.start()
+    l0 = sum(c.kernel_launches() for c in run.ctxs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(run.stream)
+    for _ in range(args.steps):
+        one()
+    e1.record(run.stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sum(c.kernel_launches() for c in run.ctxs) - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    updates = 6 * n * n * npz * nq
+    cells_rank = len(run.mine) * mo.m * mo.m * npz
+
+    for c in run.ctxs:
+        c.profile_enable(True)
+    for _ in range(2):
+        one()
+    prof = {k: sum(c.profile_get(k)[0] for c in run.ctxs) / 2 for k in ("advect", "remap", "halo", "cmax", "scale")}
+    adv_n = sum(c.profile_get("advect")[1] for c in run.ctxs)
+    for c in run.ctxs:
+        c.profile_enable(False)
+    barrier()
+    roof = None
+    if rank == 0:
+        peak, which = 6650.0, "fallback"
+        try:
+            peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+            which = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+        adv_bytes = cells_rank * (2 * w * nq + 5 * w)
+        ach = adv_bytes / (prof["advect"] * 1e-3) / 1e9
+        B = 2 * w * 2 + w * 7 / nq
+        roof = {"bound": "hbm", "kernel": "k_advect5", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": which, "bytes_per_launch": adv_bytes / max(adv_n // 2, 1) * 1.0, "avg_launch_ms": prof["advect"] / max(adv_n // 2, 1),
+                "rank0_ms_per_step": {"advect": prof["advect"], "remap": prof["remap"], "halo gather/scatter kernels": prof["halo"],
+                                      "prep/coef/cmax": prof["cmax"] + prof["scale"]},
+                "step_frac_of_roofline_per_gpu": (updates / world / (ms_max / args.steps * 1e-3)) * B / (peak * 1e9)}
+
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        from .devarray import field_shape
+        fields_in = ["q", "dp1", "mfx", "mfy", "cx", "cy", "pe"]
+        tdt = run.tdt
+        host = [{f: torch.empty(field_shape(c, f, nq), dtype=tdt, pin_memory=True) for f in fields_in + ["delp"]} for c in run.ctxs]
+        fill_submosaic(run, grid, args, local_rank)
+        for c, h in zip(run.ctxs, host):
+            for f in fields_in:
+                c.download_ptr(f, h[f].data_ptr(), nq)
+        run.stream.synchronize()
+
+        def e2e_step():
+            for c, h in zip(run.ctxs, host):
+                for f in fields_in:
+                    c.upload_ptr(f, h[f].data_ptr(), nq)
+                c.set_vertical(ak, bk, ptop)
+            one()
+            for c, h in zip(run.ctxs, host):
+                c.download_ptr("q", h["q"].data_ptr(), nq)
+                c.download_ptr("delp", h["delp"].data_ptr(), nq)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        et = torch.tensor([wall, sum(h[f].numel() * w for h in host for f in fields_in),
+                           sum((h["q"].numel() + h["delp"].numel()) * w for h in host)], dtype=torch.float64, device=dev)
+        mx = et.clone()
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(et)
+        e2e = {"value": updates * args.e2e_steps / (float(mx[0].item()) * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(et[1].item()),
+               "d2h_bytes_per_step": int(et[2].item()), "steps": args.e2e_steps, "ms_per_step": float(mx[0].item()) / args.e2e_steps}
+        del host
+    if rank == 0:
+        line = {"metric": "tracer_cell_updates_per_s", "value": updates * args.steps / (ms_max * 1e-3), "unit": "cell-updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if w == 8 else "f32", "data": "synthetic",
+                "config": {"workload": f"C{n} L{npz}, {nq} tracers in total, {args.dtype}, hord_tr={args.hord}, kord_tr={args.kord}, fill, "
+                                       f"tracer_2d + tracer remap",
+                           "parallelism": f"ONE problem as {len(mo)} sub-domains (layout {L}x{L} per tile, C{mo.m} each), {len(run.mine)} per rank in "
+                                          f"{len(run.ctxs)} sub-tile context(s), all {nq} tracers on every rank",
+                           "halo": f"per sub-step one packed NCCL send/recv per peer pair ({len(run.plan.sends)} peers of rank 0, {run.halo_bytes} B sent by "
+                                   f"rank 0: side halos + diagonal blocks as gather lists) + all-reduce(max) of cmax",
+                           "halo_bytes_sent_per_rank_and_substep": run.halo_bytes, "nsplt": int(nsplt), "updates_per_step": updates,
+                           "l2": "inputs (GBs per rank) far exceed the 126 MB L2; no flush needed"},
+                "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": None, "clocks": clocks}
+        print(json.dumps(line))
+    run.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
