@@ -167,7 +167,7 @@ template <class T> struct Impl {
   int sub_L = 0;               // sub-tile context: layout L x L per tile (0: whole tiles); flags per resident sub-domain
   fv3t::A5Sub subflags[6];
   std::vector<int*> lists;     // gather / scatter lists (fv3t_halo_list_create)
-  std::vector<int> list_len;
+  std::vector<int> list_len, list_max;
   // host state
   std::vector<int> ksplt, cpy;
   std::vector<T> cmax_h;
@@ -250,7 +250,7 @@ template <class T> struct Impl {
   int substep(int it, int hord, T lim_fac);
   int prepare(int hord, bool allow5 = true);
   int apply_damping(int it, bool mf_scaled);
-  int halo_list_move(int it, int lt, int list, T* buf, bool scatter);
+  int halo_list_move(int it, int lt, int list, T* buf, bool scatter, int stride);
   int halo_list_create(const int* offs, int count, int* list);
   int halo_local_table(const int* dst, const int* src, int len);
   int fv_tp_2d_host(int nlev, T* q, const T* crx, const T* cry, int hord, T* fx, T* fy, const T* xfx, const T* yfx, const T* ra_x,
@@ -497,15 +497,34 @@ template <class T> int Impl<T>::halo_local(int it) {
 
 template <class T>
 __global__ void k_strip(T* __restrict__ q, T* __restrict__ buf, const int* __restrict__ idx, int n, int npz, int nq,
-                        const int* __restrict__ ksplt, int it, int unpack, int len) {
+                        const int* __restrict__ ksplt, int it, int unpack, int len, int stride) {
   const long plane = (long)(n + 6) * (n + 6);
   const int pl = blockIdx.y;  // iq*npz + kz
   if (it > ksplt[pl % npz]) return;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < len; e += gridDim.x * blockDim.x) {
     if (unpack)
-      q[(long)pl * plane + idx[e]] = buf[(long)pl * len + e];
+      q[(long)pl * plane + idx[e]] = buf[(long)pl * stride + e];
     else
-      buf[(long)pl * len + e] = q[(long)pl * plane + idx[e]];
+      buf[(long)pl * stride + e] = q[(long)pl * plane + idx[e]];
+  }
+}
+
+// the same for a list of FLAT offsets into the stack of resident tiles (local_tile * plane + offset): one launch moves the cells
+// of several resident tiles
+template <class T>
+__global__ void k_strip_flat(T* __restrict__ q, T* __restrict__ buf, const int* __restrict__ idx, int n, int npz, int nq,
+                             const int* __restrict__ ksplt, int it, int unpack, int len, int stride) {
+  const int plane = (n + 6) * (n + 6);
+  const long tile_stride = (long)plane * npz * nq;
+  const int pl = blockIdx.y;
+  if (it > ksplt[pl % npz]) return;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < len; e += gridDim.x * blockDim.x) {
+    const int o = idx[e];
+    const long a = (long)(o / plane) * tile_stride + (long)pl * plane + o % plane;
+    if (unpack)
+      q[a] = buf[(long)pl * stride + e];
+    else
+      buf[(long)pl * stride + e] = q[a];
   }
 }
 
@@ -517,7 +536,7 @@ template <class T> int Impl<T>::halo_pack(int it, int lt, int edge, T* buf, bool
   T* qt = q[(cur + it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
   kbegin();
   k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, unpack ? strip_halo[lt][edge] : strip_idx[lt][edge], n, npz, nq_cur, ksplt_d, it,
-                                       unpack ? 1 : 0, 3 * n);
+                                       unpack ? 1 : 0, 3 * n, 3 * n);
   kend(KC_HALO);
   CK(cudaGetLastError());
   return 0;
@@ -525,9 +544,12 @@ template <class T> int Impl<T>::halo_pack(int it, int lt, int edge, T* buf, bool
 
 template <class T> int Impl<T>::halo_list_create(const int* offs, int count, int* list) {
   if (!list || count < 0 || (count > 0 && !offs)) return fail("fv3tracer: halo_list_create: bad arguments");
-  const int pl = (int)plane();
-  for (int e = 0; e < count; ++e)
-    if (offs[e] < 0 || offs[e] >= pl) return fail("fv3tracer: halo_list_create: offset %d outside the plane (%d cells)", offs[e], pl);
+  const long pl = (long)plane() * nt;
+  int mx = 0;
+  for (int e = 0; e < count; ++e) {
+    if (offs[e] < 0 || offs[e] >= pl) return fail("fv3tracer: halo_list_create: offset %d outside the resident planes (%ld cells)", offs[e], pl);
+    mx = std::max(mx, offs[e]);
+  }
   CK(cudaSetDevice(device));
   int* d = nullptr;
   if (count) {
@@ -536,6 +558,7 @@ template <class T> int Impl<T>::halo_list_create(const int* offs, int count, int
   }
   lists.push_back(d);
   list_len.push_back(count);
+  list_max.push_back(mx);
   *list = (int)lists.size() - 1;
   return 0;
 }
@@ -561,18 +584,24 @@ template <class T> int Impl<T>::halo_local_table(const int* dst, const int* src,
 }
 
 // generic gather (scatter) of the cells named by a registered list, every plane of the resident tracers of one resident tile
-template <class T> int Impl<T>::halo_list_move(int it, int lt, int list, T* buf, bool scatter) {
-  if (lt < 0 || lt >= nt) return fail("fv3tracer: bad local tile %d", lt);
+template <class T> int Impl<T>::halo_list_move(int it, int lt, int list, T* buf, bool scatter, int stride) {
+  if (lt < -1 || lt >= nt) return fail("fv3tracer: bad local tile %d", lt);
   if (list < 0 || list >= (int)lists.size()) return fail("fv3tracer: unknown halo list %d", list);
+  if (lt >= 0 && list_max[list] >= (int)plane()) return fail("fv3tracer: halo list %d holds flat offsets: use local_tile = -1", list);
   if (!buf) return fail("fv3tracer: halo_gather / halo_scatter: null buffer");
   if (nq_cur < 1) return fail("fv3tracer: no resident tracers");
   const int len = list_len[list];
   if (len == 0) return 0;
+  if (stride == 0) stride = len;
+  if (stride < len) return fail("fv3tracer: halo_gather / halo_scatter: buffer stride %d shorter than the list (%d)", stride, len);
   CK(cudaSetDevice(device));
   dim3 grid((len + 255) / 256, nq_cur * npz);
-  T* qt = q[(cur + it - 1) & 1] + (size_t)lt * sz_q(nq_cur);
+  T* qt = q[(cur + it - 1) & 1] + (size_t)(lt < 0 ? 0 : lt) * sz_q(nq_cur);
   kbegin();
-  k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, lists[list], n, npz, nq_cur, ksplt_d, it, scatter ? 1 : 0, len);
+  if (lt < 0)
+    k_strip_flat<T><<<grid, 256, 0, stream>>>(qt, buf, lists[list], n, npz, nq_cur, ksplt_d, it, scatter ? 1 : 0, len, stride);
+  else
+    k_strip<T><<<grid, 256, 0, stream>>>(qt, buf, lists[list], n, npz, nq_cur, ksplt_d, it, scatter ? 1 : 0, len, stride);
   kend(KC_HALO);
   CK(cudaGetLastError());
   return 0;
@@ -1673,13 +1702,14 @@ extern "C" int fv3t_device_count(void) {
     CK(cudaStreamSynchronize(I->stream));                                                                                      \
     return 0;                                                                                                                  \
   }                                                                                                                            \
-  extern "C" int fv3t_##P##_halo_gather(fv3t_ctx* ctx, int it, int local_tile, int list, REAL* dev_buf) {                     \
+  extern "C" int fv3t_##P##_halo_gather(fv3t_ctx* ctx, int it, int local_tile, int list, REAL* dev_buf, int buf_stride) {     \
     NEED(ctx, P);                                                                                                              \
-    return I->halo_list_move(it, local_tile, list, dev_buf, false);                                                            \
+    return I->halo_list_move(it, local_tile, list, dev_buf, false, buf_stride);                                                \
   }                                                                                                                            \
-  extern "C" int fv3t_##P##_halo_scatter(fv3t_ctx* ctx, int it, int local_tile, int list, const REAL* dev_buf) {              \
+  extern "C" int fv3t_##P##_halo_scatter(fv3t_ctx* ctx, int it, int local_tile, int list, const REAL* dev_buf,                 \
+                                         int buf_stride) {                                                                     \
     NEED(ctx, P);                                                                                                              \
-    return I->halo_list_move(it, local_tile, list, const_cast<REAL*>(dev_buf), true);                                          \
+    return I->halo_list_move(it, local_tile, list, const_cast<REAL*>(dev_buf), true, buf_stride);                              \
   }                                                                                                                            \
   extern "C" int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac) {                                 \
     NEED(ctx, P);                                                                                                              \

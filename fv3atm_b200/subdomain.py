@@ -192,26 +192,40 @@ class ExchangePlan:
                 self.recvs.setdefault(rs, []).append((cd, ld, doff))
         for c, (a, b) in loc.items():
             self.local[c] = (np.concatenate(a).astype(np.int32), np.concatenate(b).astype(np.int32))
+        # consecutive pieces of a message that live in the same context become ONE flat list (local_tile = -1): one gather / scatter
+        # launch per context and peer instead of one per pair of sub-domains
+        def merge(pieces):
+            out = []
+            for c, lt, offs in pieces:
+                flat = offs.astype(np.int64) + lt * plane
+                if out and out[-1][0] == c:
+                    out[-1][1].append(flat)
+                else:
+                    out.append([c, [flat]])
+            return [(c, -1, np.concatenate(fl).astype(np.int32)) for c, fl in out]
+        self.sends = {p: merge(v) for p, v in self.sends.items()}
+        self.recvs = {p: merge(v) for p, v in self.recvs.items()}
 
     def message_cells(self, peer: int, sending: bool) -> int:
         return sum(len(o) for _, _, o in (self.sends if sending else self.recvs).get(peer, []))
 
 
 def run_exchange(plan: ExchangePlan, planes: int, copy_buf, sbuf: dict, rbuf: dict, gather, scatter, group=None):
-    """The cross-context and cross-rank part of one halo update.  gather(ctx, local_tile, offsets, view) fills a flat buffer view
-    with `planes x len(offsets)` values, scatter is its inverse; the buffers are torch tensors (CUDA with NCCL, CPU with gloo)."""
+    """The cross-context and cross-rank part of one halo update.  gather(ctx, local_tile, offsets, buf, at, stride) writes
+    buf[pl * stride + at + e] for every plane pl and list entry e, scatter is its inverse; a message is plane-major over ALL its
+    cells (stride = cells of the message), so its layout does not depend on how either side groups the pieces into launches.
+    The buffers are flat torch tensors (CUDA with NCCL, CPU with gloo)."""
     for (cs_, ls, soff, cd, ld, doff) in plan.copies:
-        v = copy_buf[:planes * len(soff)]
-        gather(cs_, ls, soff, v)
-        scatter(cd, ld, doff, v)
+        gather(cs_, ls, soff, copy_buf, 0, len(soff))
+        scatter(cd, ld, doff, copy_buf, 0, len(soff))
     if not plan.sends and not plan.recvs:
         return
     import torch.distributed as dist
     for p, pieces in plan.sends.items():
-        at = 0
+        at, total = 0, plan.message_cells(p, True)
         for (c, lt, offs) in pieces:
-            gather(c, lt, offs, sbuf[p][at:at + planes * len(offs)])
-            at += planes * len(offs)
+            gather(c, lt, offs, sbuf[p], at, total)
+            at += len(offs)
     ops = []
     for p in sorted(set(plan.sends) | set(plan.recvs)):
         for kind in ((0, 1) if plan.rank < p else (1, 0)):  # both ends of a pair enqueue in one order
@@ -222,10 +236,10 @@ def run_exchange(plan: ExchangePlan, planes: int, copy_buf, sbuf: dict, rbuf: di
     for w in dist.batch_isend_irecv(ops):
         w.wait()
     for p, pieces in plan.recvs.items():
-        at = 0
+        at, total = 0, plan.message_cells(p, False)
         for (c, lt, offs) in pieces:
-            scatter(c, lt, offs, rbuf[p][at:at + planes * len(offs)])
-            at += planes * len(offs)
+            scatter(c, lt, offs, rbuf[p], at, total)
+            at += len(offs)
 
 
 class SubMosaicStep:
@@ -309,12 +323,17 @@ class SubMosaicStep:
     def _exchange(self, it: int):
         for ctx in self.ctxs:
             ctx.halo_local(it)
-        gather = lambda c, lt, offs, view: self.ctxs[c].halo_gather(it, lt, self._list(c, offs), view.data_ptr())
-        scatter = lambda c, lt, offs, view: self.ctxs[c].halo_scatter(it, lt, self._list(c, offs), view.data_ptr())
+        esz = self.cmax_dev.element_size()
+        gather = lambda c, lt, offs, buf, at, stride: self.ctxs[c].halo_gather(it, lt, self._list(c, offs), buf.data_ptr() + at * esz, stride)
+        scatter = lambda c, lt, offs, buf, at, stride: self.ctxs[c].halo_scatter(it, lt, self._list(c, offs), buf.data_ptr() + at * esz, stride)
         run_exchange(self.plan, self.npz * self.nq, self.copy_buf, self.sbuf, self.rbuf, gather, scatter, self.group)
 
     def tracer_2d(self, hord: int, q_split: int = 0, lim_fac: float = 1.0) -> int:
         torch = self.torch
+        # The halo update of the first sub-step needs neither cmax nor ksplt (every level takes part, and outside a tracer_2d call
+        # every level lives in the current buffer): it is queued FIRST, behind whatever the stream is still running, so that its
+        # launches and the NCCL transfer overlap the host round trips of the cmax reduction instead of following them.
+        self.exchange(1)
         cm = None
         for ctx in self.ctxs:
             c = ctx.tracer_2d_begin(self.nq, q_split)
@@ -329,7 +348,8 @@ class SubMosaicStep:
         for ctx in self.ctxs:
             nsplt = ctx.tracer_2d_set_cmax(cm, q_split)
         for it in range(1, nsplt + 1):
-            self.exchange(it)
+            if it > 1:
+                self.exchange(it)
             for ctx in self.ctxs:
                 ctx.tracer_2d_substep(it, hord, lim_fac)
         for ctx in self.ctxs:

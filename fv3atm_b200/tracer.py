@@ -221,11 +221,11 @@ class TracerContext:
         assert dst.size == src.size
         L.check(L.load().fv3t_halo_local_table(self._h, L.ptr(dst), L.ptr(src), int(dst.size)))
 
-    def halo_gather(self, it, local_tile, list_id, dev_ptr):
-        L.check(self._f("halo_gather")(self._h, int(it), int(local_tile), int(list_id), C.c_void_p(dev_ptr)))
+    def halo_gather(self, it, local_tile, list_id, dev_ptr, stride=0):
+        L.check(self._f("halo_gather")(self._h, int(it), int(local_tile), int(list_id), C.c_void_p(dev_ptr), int(stride)))
 
-    def halo_scatter(self, it, local_tile, list_id, dev_ptr):
-        L.check(self._f("halo_scatter")(self._h, int(it), int(local_tile), int(list_id), C.c_void_p(dev_ptr)))
+    def halo_scatter(self, it, local_tile, list_id, dev_ptr, stride=0):
+        L.check(self._f("halo_scatter")(self._h, int(it), int(local_tile), int(list_id), C.c_void_p(dev_ptr), int(stride)))
 
     def tracer_2d_substep(self, it, hord, lim_fac=1.0):
         L.check(self._f("tracer_2d_substep")(self._h, int(it), int(hord), self._ct(lim_fac)))

@@ -193,11 +193,13 @@ int fv3t_device_count(void);
   int fv3t_##P##_halo_pack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, REAL* host_buf);                        \
   int fv3t_##P##_halo_unpack_host(fv3t_ctx* ctx, int it, int local_tile, int edge, const REAL* host_buf);                \
   /* Generic halo exchange by gather list (sub-tile contexts; works for whole tiles too): `list` names a set of plane offsets    \
-     (row-major (j+2)*(npx+5) + (i+2)) registered with fv3t_halo_list_create.  gather: dev_buf[pl*count + e] = q_in(it)[tile     \
-     local_tile][plane pl][offset e] for the planes pl = iq*npz + k of the resident tracers; scatter is the inverse.  Levels    \
-     whose ksplt(k) < it are skipped on both sides, like the strips above. */                                                  \
-  int fv3t_##P##_halo_gather(fv3t_ctx* ctx, int it, int local_tile, int list, REAL* dev_buf);                            \
-  int fv3t_##P##_halo_scatter(fv3t_ctx* ctx, int it, int local_tile, int list, const REAL* dev_buf);                     \
+     (row-major (j+2)*(npx+5) + (i+2)) registered with fv3t_halo_list_create.  gather: dev_buf[pl*buf_stride + e] = q_in(it)     \
+     [tile local_tile][plane pl][offset e] for the planes pl = iq*npz + k of the resident tracers; scatter is the inverse.      \
+     buf_stride = 0 stands for the length of the list; a larger stride lets several lists share one plane-major message.  Levels \
+     whose ksplt(k) < it are skipped on both sides, like the strips above.  local_tile = -1: the list holds FLAT offsets         \
+     local_tile * (npx+5)^2 + offset into the stack of resident tiles (one launch for the cells of several tiles). */          \
+  int fv3t_##P##_halo_gather(fv3t_ctx* ctx, int it, int local_tile, int list, REAL* dev_buf, int buf_stride);            \
+  int fv3t_##P##_halo_scatter(fv3t_ctx* ctx, int it, int local_tile, int list, const REAL* dev_buf, int buf_stride);     \
   int fv3t_##P##_tracer_2d_substep(fv3t_ctx* ctx, int it, int hord, REAL lim_fac);                                      \
   int fv3t_##P##_tracer_2d_finish(fv3t_ctx* ctx);
 

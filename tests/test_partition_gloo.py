@@ -150,7 +150,7 @@ def test_submosaic_assignment_and_plan_consistency():
         for r, pl in enumerate(plans):
             cells += sum(len(d) for d, _ in pl.local.values()) + sum(len(o) for *_, o in pl.copies)
             for p in pl.sends:
-                assert [len(o) for _, _, o in pl.sends[p]] == [len(o) for _, _, o in plans[p].recvs[r]]
+                assert pl.message_cells(p, True) == plans[p].message_cells(r, False)    # (pieces are merged per context: totals match)
                 cells += pl.message_cells(p, True)
         assert cells == total          # every halo cell is filled exactly once, by exactly one of the three mechanisms
     with pytest.raises(ValueError):
@@ -187,11 +187,16 @@ def _sub_worker(rank, world, port, n, L, planes, out_dir):
             flat[:, dst] = flat[:, src]
             ctx[c][:] = flat.reshape(planes, ctx[c].shape[0], md, md).transpose(1, 0, 2, 3)
 
-        def gather(c, lt, offs, view):
-            view.copy_(torch.from_numpy(np.ascontiguousarray(ctx[c][lt].reshape(planes, -1)[:, offs]).ravel()))
+        def cells(lt, offs):   # lt = -1: flat offsets local_tile * plane + offset (fv3t_*_halo_gather's rule)
+            return (np.full(len(offs), lt), offs) if lt >= 0 else np.divmod(offs, md * md)
 
-        def scatter(c, lt, offs, view):
-            ctx[c][lt].reshape(planes, -1)[:, offs] = view.numpy().reshape(planes, len(offs))
+        def gather(c, lt, offs, buf, at, stride):
+            tt, r = cells(lt, offs)
+            buf.numpy()[:planes * stride].reshape(planes, stride)[:, at:at + len(offs)] = ctx[c].reshape(-1, planes, md * md)[tt, :, r].T
+
+        def scatter(c, lt, offs, buf, at, stride):
+            tt, r = cells(lt, offs)
+            ctx[c].reshape(-1, planes, md * md)[tt, :, r] = buf.numpy()[:planes * stride].reshape(planes, stride)[:, at:at + len(offs)].T
 
         mk = lambda ne: torch.empty(max(ne, 1), dtype=torch.float64)
         copy_buf = mk(planes * max([len(o) for *_, o in plan.copies] + [0]))
