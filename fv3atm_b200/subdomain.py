@@ -333,11 +333,17 @@ class SubMosaicStep:
         # The halo update of the first sub-step needs neither cmax nor ksplt (every level takes part, and outside a tracer_2d call
         # every level lives in the current buffer): it is queued FIRST, behind whatever the stream is still running, so that its
         # launches and the NCCL transfer overlap the host round trips of the cmax reduction instead of following them.
-        self.exchange(1)
+        # (Not on the very first call: tracer_2d_begin is what tells a context how many tracers are resident.)
+        early = getattr(self, "_primed", False)
+        if early:
+            self.exchange(1)
         cm = None
         for ctx in self.ctxs:
             c = ctx.tracer_2d_begin(self.nq, q_split)
             cm = c if cm is None else np.maximum(cm, c)
+        self._primed = True
+        if not early:
+            self.exchange(1)
         if self.world > 1 and q_split == 0:
             import torch.distributed as dist
             with torch.cuda.stream(self.stream):
