@@ -7,10 +7,10 @@ C768 L127, fp64, 9 GFS tracers, hord_tr = 8, kord_tr = 9.  One tracer cell-updat
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 
-N = 1: the whole C768 L127 x 9-tracer mosaic on one GPU.  N > 1 (torchrun, one rank per GPU): tracer-group
-sharding -- every rank owns all six faces of its own group of 9 tracers with winds / mass fluxes / delp
-replicated, so there is no data-path collective (weak scaling in the number of tracers).
-`--shard face` instead splits the six faces of ONE 9-tracer problem over the ranks with NCCL send/recv halos.
+N = 1: the whole C768 L127 x 9-tracer mosaic on one GPU.  N > 1 (torchrun, one rank per GPU): the SAME problem split over
+the ranks (strong scaling, BASELINE config 4): N >= 4 dividing 24 -> 24 square sub-domains (layout 2 x 2 per tile, SURVEY.md
+8e) in sub-tile contexts, halos as packed gather lists over NCCL; otherwise whole tiles split by faces x tracer groups with
+NCCL edge strips (`--shard face`).  `--shard tracer` runs replicas instead (every rank its own 9 tracers, weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events on the context's stream, max
 over ranks); `e2e` goes through the host-array C-ABI path (pinned host buffers, H2D + D2H inside the timed
@@ -52,9 +52,11 @@ def parse():
     ap.add_argument("--kord", type=int, default=9)
     ap.add_argument("--courant", type=float, default=0.7)
     ap.add_argument("--sub-layout", type=int, default=2, help="--shard sub: L x L sub-domains per tile")
-    ap.add_argument("--shard", default="face", choices=["tracer", "face", "group", "sub"],
-                    help="N > 1 ranks.  face (default) / group: ONE nq-tracer problem split by faces x tracer groups / by tracer groups only "
-                         "(strong scaling, BASELINE config 4 / 5); tracer: every rank its own nq tracers (replicas, weak)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "tracer", "face", "group", "sub"],
+                    help="N > 1 ranks, ONE nq-tracer problem (strong scaling, BASELINE config 4 / 5).  sub: --sub-layout^2 square sub-domains "
+                         "per tile in sub-tile contexts (24 for the default 2 x 2: SURVEY.md 8e); face / group: whole tiles split by faces x "
+                         "tracer groups / by tracer groups only; auto (default): sub when N >= 4 divides the sub-domain count, else face.  "
+                         "tracer: every rank its own nq tracers (replicas, weak)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of a level subset of the workload")
@@ -295,6 +297,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.shard == "auto":
+        nsub = 6 * args.sub_layout * args.sub_layout
+        args.shard = "sub" if (world >= 4 and nsub % world == 0 and nsub // world <= 6 and args.n % args.sub_layout == 0) else "face"
     if args.shard == "sub":
         from fv3atm_b200 import subdomain
         args.clock_sampler = ClockSampler

@@ -460,6 +460,33 @@ def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
     updates = 6 * n * n * npz * nq
     cells_rank = len(run.mine) * mo.m * mo.m * npz
 
+    # where the step time goes besides the kernels: the halo update alone and the cmax reduction alone (events on the stream)
+    def timed(fn, reps=10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(run.stream)
+        for _ in range(reps):
+            fn()
+        b.record(run.stream)
+        barrier()
+        v = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    def cmax_only():
+        cm = None
+        for ctx in run.ctxs:
+            c = ctx.tracer_2d_begin(nq, 0)
+            cm = c if cm is None else np.maximum(cm, c)
+        if world > 1:
+            with torch.cuda.stream(run.stream):
+                run.cmax_dev.copy_(torch.from_numpy(np.ascontiguousarray(cm)))
+                dist.all_reduce(run.cmax_dev, op=dist.ReduceOp.MAX)
+                run.cmax_dev.cpu()
+
+    exchange_ms = timed(lambda: run.exchange(1))
+    cmax_ms = timed(cmax_only)
     for c in run.ctxs:
         c.profile_enable(True)
     for _ in range(2):
@@ -469,6 +496,14 @@ def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
     for c in run.ctxs:
         c.profile_enable(False)
     barrier()
+    # kernel time per step of EVERY rank (the ranks meet twice per step, so the slowest one sets the pace)
+    ksum = torch.tensor([sum(prof.values())], dtype=torch.float64, device=dev)
+    kall = [torch.zeros_like(ksum) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(kall, ksum)
+    else:
+        kall = [ksum]
+    kernel_ms_by_rank = [round(float(v.item()), 3) for v in kall]
     roof = None
     if rank == 0:
         peak, which = 6650.0, "fallback"
@@ -534,7 +569,9 @@ def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
                                           f"{len(run.ctxs)} sub-tile context(s), all {nq} tracers on every rank",
                            "halo": f"per sub-step one packed NCCL send/recv per peer pair ({len(run.plan.sends)} peers of rank 0, {run.halo_bytes} B sent by "
                                    f"rank 0: side halos + diagonal blocks as gather lists) + all-reduce(max) of cmax",
-                           "halo_bytes_sent_per_rank_and_substep": run.halo_bytes, "nsplt": int(nsplt), "updates_per_step": updates,
+                           "halo_bytes_sent_per_rank_and_substep": run.halo_bytes, "halo_update_ms": exchange_ms, "cmax_reduction_ms": cmax_ms,
+                           "kernel_ms_per_step_by_rank": kernel_ms_by_rank,
+                           "nsplt": int(nsplt), "updates_per_step": updates,
                            "l2": "inputs (GBs per rank) far exceed the 126 MB L2; no flush needed"},
                 "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": None, "clocks": clocks}
         print(json.dumps(line))

@@ -8,7 +8,7 @@ python - <<P
 import json
 try:
     d=json.loads(open("gpurun_out/bench_${NG}gpu_$sh.json").read().strip().splitlines()[-1])
-    print("$sh", d["n_gpus"], d["ms_per_step"], d["e2e"]["ms_per_step"] if d.get("e2e") else None, d["roofline"]["rank0_ms_per_step"], d["config"]["halo_bytes_sent_per_rank_and_substep"])
+    print("$sh", d["n_gpus"], d["ms_per_step"], d["e2e"]["ms_per_step"] if d.get("e2e") else None, d["roofline"]["rank0_ms_per_step"], d["config"]["halo_bytes_sent_per_rank_and_substep"], d["config"].get("halo_update_ms"), d["config"].get("cmax_reduction_ms"))
 except Exception as e:
     print("ERR $sh", e); print(open("gpurun_out/bench_${NG}gpu_$sh.err").read()[-2500:])
 P
