@@ -12,6 +12,8 @@ module fv3tracer_iface_mod
   public :: fv3t_upload, fv3t_download, fv3t_set_vertical, fv3t_tracer_2d_begin, fv3t_tracer_2d_set_cmax, fv3t_halo_local
   public :: fv3t_halo_pack_host, fv3t_halo_unpack_host, fv3t_tracer_2d_substep, fv3t_tracer_2d_finish
   public :: fv3t_tracer_2d_resident, fv3t_remap_tracers_resident, fv3t_remap_prepare
+  public :: fv3t_set_damping, fv3t_map_scalar, fv3t_map1_ppm, fv3t_map_field, fv3t_fv_tp_2d
+  public :: fv3t_halo_list_create, fv3t_halo_list_count, fv3t_halo_local_table, fv3t_halo_gather, fv3t_halo_scatter
   public :: FV3T_Q, FV3T_DP1, FV3T_MFX, FV3T_MFY, FV3T_CX, FV3T_CY, FV3T_PE, FV3T_DELP
 
 #ifdef OVERLOAD_R4
@@ -27,6 +29,10 @@ module fv3tracer_iface_mod
   type, bind(C) :: fv3t_dims
     integer(c_int) :: npx, npz, nq_max, ntiles
     integer(c_int) :: tile_id(6)
+    !> sub-tile contexts (layout > 1,1: bd%is..ie a proper sub-range of the tile): sub_layout = L, block (sub_bi, sub_bj) of every
+    !! resident sub-domain, npx = LOCAL extent + 1; 0 = whole tiles
+    integer(c_int) :: sub_layout = 0
+    integer(c_int) :: sub_bi(6) = 0, sub_bj(6) = 0
   end type fv3t_dims
 
   type, bind(C) :: fv3t_grid
@@ -171,6 +177,77 @@ module fv3tracer_iface_mod
     integer(c_int) function fv3t_remap_prepare(ctx) bind(C, name=FV3T_P//'remap_prepare')
       import :: c_ptr, c_int
       type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function fv3t_set_damping(ctx, del6_u, del6_v, da_min, nord_tr, trdm) bind(C, name=FV3T_P//'set_damping')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: del6_u, del6_v        ! c_loc of gridstruct%del6_u / del6_v, or c_null_ptr to keep the metrics
+      real(fv3t_real), value :: da_min, trdm
+      integer(c_int), value :: nord_tr
+    end function
+    integer(c_int) function fv3t_map_scalar(ctx, q, qs, iv, kord, q_min) bind(C, name=FV3T_P//'map_scalar')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      real(fv3t_real), intent(inout) :: q(*)
+      type(c_ptr), value :: qs                     ! c_loc(qs) for iv = -2, else c_null_ptr
+      integer(c_int), value :: iv, kord
+      real(fv3t_real), value :: q_min
+    end function
+    integer(c_int) function fv3t_map1_ppm(ctx, q, qs, iv, kord) bind(C, name=FV3T_P//'map1_ppm')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      real(fv3t_real), intent(inout) :: q(*)
+      type(c_ptr), value :: qs
+      integer(c_int), value :: iv, kord
+    end function
+    integer(c_int) function fv3t_map_field(ctx, q, qs, iv, kord, q_min, use_cs) bind(C, name=FV3T_P//'map_field')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      real(fv3t_real), intent(inout) :: q(*)
+      type(c_ptr), value :: qs
+      integer(c_int), value :: iv, kord, use_cs
+      real(fv3t_real), value :: q_min
+    end function
+    !> fv_tp_2d (tp_core.F90:110-133); the Fortran optionals arrive as c_null_ptr / nord < 0
+    integer(c_int) function fv3t_fv_tp_2d(ctx, nlev, q, crx, cry, hord, fx, fy, xfx, yfx, ra_x, ra_y, lim_fac, mfx, mfy, mass, nord, &
+                                          damp_c) bind(C, name=FV3T_P//'fv_tp_2d')
+      import :: c_ptr, c_int, fv3t_real
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nlev, hord, nord
+      real(fv3t_real), intent(inout) :: q(*)
+      real(fv3t_real), intent(in) :: crx(*), cry(*), xfx(*), yfx(*), ra_x(*), ra_y(*)
+      real(fv3t_real), intent(out) :: fx(*), fy(*)
+      real(fv3t_real), value :: lim_fac, damp_c
+      type(c_ptr), value :: mfx, mfy, mass
+    end function
+    !> generic halo exchange by gather list (sub-tile contexts); dev_buf is a DEVICE address (CUDA-aware MPI / NCCL)
+    integer(c_int) function fv3t_halo_list_create(ctx, offsets, count, list) bind(C, name='fv3t_halo_list_create')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), intent(in) :: offsets(*)
+      integer(c_int), value :: count
+      integer(c_int), intent(out) :: list
+    end function
+    integer(c_int) function fv3t_halo_list_count(ctx, list) bind(C, name='fv3t_halo_list_count')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: list
+    end function
+    integer(c_int) function fv3t_halo_local_table(ctx, dst, src, len) bind(C, name='fv3t_halo_local_table')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), intent(in) :: dst(*), src(*)
+      integer(c_int), value :: len
+    end function
+    integer(c_int) function fv3t_halo_gather(ctx, it, local_tile, list, dev_buf, buf_stride) bind(C, name=FV3T_P//'halo_gather')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, dev_buf
+      integer(c_int), value :: it, local_tile, list, buf_stride
+    end function
+    integer(c_int) function fv3t_halo_scatter(ctx, it, local_tile, list, dev_buf, buf_stride) bind(C, name=FV3T_P//'halo_scatter')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, dev_buf
+      integer(c_int), value :: it, local_tile, list, buf_stride
     end function
     integer(c_int) function fv3t_neighbor(ctx, global_tile, edge, nbr_tile, nbr_edge, rotated) bind(C, name='fv3t_neighbor')
       import :: c_ptr, c_int

@@ -266,6 +266,36 @@ int main(void) {
     CHECK(changed > 0 && wrong == 0, "pack_host -> unpack_host fills the neighbour's edge halo like halo_local");
     free(strip), free(qh), free(qs);
   }
+  /* gather lists (the generic halo exchange of sub-tile contexts; valid for whole tiles too) and a sub-tile context */
+  {
+    int offs[3] = {3 * ND + 3, 3 * ND + 4, 4 * ND + 3}, flat[2] = {3 * ND + 3, (int)plane + 3 * ND + 3}, bad[1] = {6 * (int)plane}, id = -1, idf = -1;
+    OK(fv3t_halo_list_create(ctx, offs, 3, &id));
+    OK(fv3t_halo_list_create(ctx, flat, 2, &idf));
+    CHECK(id >= 0 && fv3t_halo_list_count(ctx, id) == 3 && fv3t_halo_list_count(ctx, idf) == 2 && fv3t_halo_list_count(ctx, 99) == -1, "list handles");
+    CHECK(fv3t_halo_list_create(ctx, bad, 1, &id) != 0, "offsets outside the resident planes are rejected");
+    CHECK(fv3t_f64_halo_gather(ctx, 1, 0, id, NULL, 0) != 0, "gather into a null buffer is an error");
+    CHECK(fv3t_f64_halo_gather(ctx, 1, 0, idf, (double*)fv3t_device_ptr(ctx, FV3T_DELP), 0) != 0, "a flat list needs local_tile = -1");
+    /* delp's device mirror serves as a scratch buffer: gather three cells of every plane of tile 2, put them back */
+    OK(fv3t_f64_upload(ctx, FV3T_Q, q0, NQ));
+    OK(fv3t_f64_halo_gather(ctx, 1, 1, id, (double*)fv3t_device_ptr(ctx, FV3T_DELP), 0));
+    OK(fv3t_f64_halo_gather(ctx, 1, -1, idf, (double*)fv3t_device_ptr(ctx, FV3T_DELP), 8));
+    OK(fv3t_f64_halo_scatter(ctx, 1, -1, idf, (const double*)fv3t_device_ptr(ctx, FV3T_DELP), 8));
+    OK(fv3t_f64_download(ctx, FV3T_Q, q, NQ));
+    CHECK(memcmp(q, q0, nq_el * sizeof(double)) == 0, "gather followed by scatter of the same list leaves q unchanged");
+    fv3t_dims ds = d;   /* six C12 sub-domains of a C24 mosaic */
+    ds.sub_layout = 2;
+    for (int t = 0; t < 6; ++t) ds.sub_bi[t] = t & 1, ds.sub_bj[t] = (t >> 1) & 1, ds.tile_id[t] = 1 + t / 4;
+    fv3t_ctx* cs = NULL;
+    OK(fv3t_f64_create(&cs, &ds, &g, 0, NULL));
+    CHECK(fv3t_f64_tracer_2d_resident(cs, NQ, 8, 0, 1.0, &nsplt) != 0, "a sub-tile context is driven through the building blocks");
+    int hd[1] = {2 * ND + 5}, hs[1] = {(int)plane + 9};
+    OK(fv3t_halo_local_table(cs, hd, hs, 1));
+    CHECK(fv3t_halo_local_table(cs, hd, bad, 1) != 0, "table offsets outside the resident planes are rejected");
+    ds.sub_bi[0] = 2;
+    fv3t_ctx* cbad = NULL;
+    CHECK(fv3t_f64_create(&cbad, &ds, &g, 0, NULL) != 0, "block index outside the layout");
+    OK(fv3t_destroy(cs));
+  }
   /* tracer_step: both calls in one, host arrays in and out */
   memcpy(q, q0, nq_el * sizeof(double));
   OK(fv3t_f64_tracer_step(ctx, q, dp1, mfx, mfy, cx, cy, pe, ak, bk, ptop, delp, NQ, 8, 0, 1.0, kord, 1, &nsplt));
