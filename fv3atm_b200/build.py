@@ -13,12 +13,15 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfv3tracer.so")
 # Two translation units: the strict kernels + host orchestration keep the bit-exact contract with the FMA-free oracle
 # (no contraction, IEEE division/sqrt); the production kernels (fv3t_fast.cu) are built with FMA contraction on.
-# The fast TU is compiled once per precision (two objects, in parallel): its k_advect5 instantiations dominate the build time.
+# The fast TU is compiled once per precision and the exact TU once per precision and parameter type (seven objects, in parallel):
+# the k_advect5 instantiations dominate the build time.
 SOURCES = [("fv3t_api.cu", "fv3t_api.o", ["--fmad=false"]),
            ("fv3t_fast.cu", "fv3t_fast_f64.o", ["--fmad=true", "-DFV3T_INST_F64"]),
            ("fv3t_fast.cu", "fv3t_fast_f32.o", ["--fmad=true", "-DFV3T_INST_F32"]),
-           ("fv3t_exact.cu", "fv3t_exact_f64.o", ["--fmad=false", "-DFV3T_INST_F64"]),
-           ("fv3t_exact.cu", "fv3t_exact_f32.o", ["--fmad=false", "-DFV3T_INST_F32"])]
+           ("fv3t_exact.cu", "fv3t_exact_f64.o", ["--fmad=false", "-DFV3T_INST_F64", "-DFV3T_INST_WHOLE"]),
+           ("fv3t_exact.cu", "fv3t_exact_f32.o", ["--fmad=false", "-DFV3T_INST_F32", "-DFV3T_INST_WHOLE"]),
+           ("fv3t_exact.cu", "fv3t_exact_sub_f64.o", ["--fmad=false", "-DFV3T_INST_F64", "-DFV3T_INST_SUB"]),
+           ("fv3t_exact.cu", "fv3t_exact_sub_f32.o", ["--fmad=false", "-DFV3T_INST_F32", "-DFV3T_INST_SUB"])]
 HEADERS = ["fv3t_common.cuh", "fv3t_ppm.cuh", "fv3t_advect.cuh", "fv3t_advect2.cuh", "fv3t_advect3.cuh", "fv3t_advect4.cuh", "fv3t_advect5.cuh", "fv3t_advect5_launch.cuh", "fv3t_deln.cuh", "fv3t_tp2d.cuh", "fv3t_remap4.cuh", "fv3t_remap.cuh",
            "fv3t_remap2.cuh", "fv3t_remap3.cuh", "fv3t_remap5.cuh", "fv3t_fast.h", "fv3t_fast.cu"]
 
@@ -49,6 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     procs = []
     dev = ["-DFV3T_A5_DEV"] if os.environ.get("FV3T_A5_DEV") else []  # development builds: k_advect5 for hord 8 / 10 only
+    dev += [x for x in os.environ.get("FV3T_EXTRA_DEFS", "").split() if x]  # experiments, e.g. -DFV3T_NO_SUB
     only = [x for x in os.environ.get("FV3T_BUILD_ONLY", "").split(",") if x]  # development: recompile the named objects only
     reuse = []
     for src, objname, extra in SOURCES:

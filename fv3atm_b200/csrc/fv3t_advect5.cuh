@@ -92,7 +92,13 @@ template <class T> struct Adv5Params {
   int tg;               // tracers per CTA (block = 32 + 64*tg threads)
   int iq0, nql;         // this launch advects tracers iq0 .. iq0+nql-1
   T lim_fac;
-  A5Sub sub[6];         // per resident tile; the default is a whole tile
+  static constexpr bool SUB = false;
+};
+// the parameters of the instantiations that serve sub-tile contexts: the flags of every resident sub-domain ride along.  A type of
+// its own, so that the whole-tile instantiations stay exactly what they were (the lookups cost the exact-arithmetic hord-10 kernel 6 %)
+template <class T> struct Adv5ParamsSub : Adv5Params<T> {
+  A5Sub sub[6];
+  static constexpr bool SUB = true;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -224,16 +230,28 @@ struct Adv5Cta {  // uniform over one tracer group
 };
 
 // index shift / edge position the PPM element functions see in x and in y (A5Sub); EDGE = false: nothing looks at them
-template <class T, bool EDGE> FV3T_HD int a5_shift_x(const Adv5Params<T>& p, const Adv5Cta& c) { return EDGE && p.sub[c.tile].no_w ? A5_SHIFT : 0; }
-template <class T, bool EDGE> FV3T_HD int a5_shift_y(const Adv5Params<T>& p, const Adv5Cta& c) { return EDGE && p.sub[c.tile].no_s ? A5_SHIFT : 0; }
-template <class T, bool EDGE> FV3T_HD int a5_edge_x(const Adv5Params<T>& p, const Adv5Cta& c, int sh) {
-  return EDGE && p.sub[c.tile].no_e ? A5_NOEDGE : c.npx + sh;
+template <class T, bool EDGE, class P> FV3T_HD int a5_shift_x(const P& p, const Adv5Cta& c) {
+  if constexpr (EDGE && P::SUB) return p.sub[c.tile].no_w ? A5_SHIFT : 0;
+  return 0;
 }
-template <class T, bool EDGE> FV3T_HD int a5_edge_y(const Adv5Params<T>& p, const Adv5Cta& c, int sh) {
-  return EDGE && p.sub[c.tile].no_n ? A5_NOEDGE : c.npx + sh;
+template <class T, bool EDGE, class P> FV3T_HD int a5_shift_y(const P& p, const Adv5Cta& c) {
+  if constexpr (EDGE && P::SUB) return p.sub[c.tile].no_s ? A5_SHIFT : 0;
+  return 0;
+}
+template <class T, bool EDGE, class P> FV3T_HD int a5_edge_x(const P& p, const Adv5Cta& c, int sh) {
+  if constexpr (EDGE && P::SUB) return p.sub[c.tile].no_e ? A5_NOEDGE : c.npx + sh;
+  return c.npx;
+}
+template <class T, bool EDGE, class P> FV3T_HD int a5_edge_y(const P& p, const Adv5Cta& c, int sh) {
+  if constexpr (EDGE && P::SUB) return p.sub[c.tile].no_n ? A5_NOEDGE : c.npx + sh;
+  return c.npx;
+}
+template <class P> FV3T_HD bool a5_corner_on(const P& p, const Adv5Cta& c, int bit) {
+  if constexpr (P::SUB) return (p.sub[c.tile].cmask & bit) != 0;
+  return true;
 }
 
-template <class T> FV3T_HD bool adv5_make_cta(const Adv5Params<T>& p, int strip, int levc, int iq, Adv5Cta& c) {
+template <class T, class P> FV3T_HD bool adv5_make_cta(const P& p, int strip, int levc, int iq, Adv5Cta& c) {
   const int n = p.n, npz = p.npz;
   const int lev = p.lev0 + levc;
   const int t = lev / npz, kz = lev % npz;
@@ -250,9 +268,13 @@ template <class T> FV3T_HD bool adv5_make_cta(const Adv5Params<T>& p, int strip,
   c.qoff = (((long)t * p.nq + iq) * npz + kz) * (long)nd * nd;
   // (the flags of a sub-tile context are read from the kernel parameters where the EDGE instantiations need them -- a5_shift_* --
   // and not carried in registers: the interior blocks, which never look at them, are the ones that set the register budget)
-  const A5Sub sb = p.sub[t];
   // x-faces i0 .. i0+nw evaluate cells i0-1 .. i0+nw; the tile-edge formulas apply to cells <= 2 and >= npx-2
-  c.xedge = (!sb.no_w && c.i0 - 1 <= 2) || (!sb.no_e && c.i0 + c.nw >= c.npx - 2);
+  bool w_edge = true, e_edge = true;
+  if constexpr (P::SUB) {
+    w_edge = !p.sub[t].no_w;
+    e_edge = !p.sub[t].no_e;
+  }
+  c.xedge = (w_edge && c.i0 - 1 <= 2) || (e_edge && c.i0 + c.nw >= c.npx - 2);
   return true;
 }
 
@@ -300,8 +322,8 @@ FV3T_HD Adv3Thr adv5_thread(const Adv5Cta& c, int tid) {
   return t;
 }
 
-template <class T, int OI, int OO>
-FV3T_HD void adv5_init(const Adv5Params<T>& p, const Adv5Cta& c, const Adv3Thr& t, T* group_smem, Adv5State<T, OI, OO>& s) {
+template <class T, int OI, int OO, class P>
+FV3T_HD void adv5_init(const P& p, const Adv5Cta& c, const Adv3Thr& t, T* group_smem, Adv5State<T, OI, OO>& s) {
   s.yin.init();
   s.you.init();
   s.Fy_prev = s.fys_prev = T(0);
@@ -317,8 +339,8 @@ FV3T_HD void adv5_init(const Adv5Params<T>& p, const Adv5Cta& c, const Adv3Thr& 
 // asynchronous copy of q(i, r) into its exchange row (slot PH = row step mod 4); CORNER: rows outside 1..n also fetch the dir = 2
 // view into the private slot (the x sweeps see the dir = 1 corner view of q, the y sweeps the dir = 2 view: copy_corners,
 // tp_core.F90:265-328)
-template <class T, int OI, int OO, int PH, bool CORNER>
-FV3T_HD void adv5_issue_q(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int PH, bool CORNER, class P>
+FV3T_HD void adv5_issue_q(const P& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
   const int n = c.n, nd = c.nd, npx = c.npx;
   if (!CORNER) {
     async_copy<sizeof(T)>(A5XROW(s, A5X_Q + PH), s.qg + (r + 2) * nd);
@@ -327,7 +349,7 @@ FV3T_HD void adv5_issue_q(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T,
     const int i = t.i;
     int ox = (r + 2) * nd, oy = ox;
     const int cbit = r < 1 ? (i < 1 ? 1 : 2) : (i > n ? 4 : 8);
-    if (t.icor && (r < 1 || r > n) && i <= n + 3 && (p.sub[c.tile].cmask & cbit)) {
+    if (t.icor && (r < 1 || r > n) && i <= n + 3 && a5_corner_on(p, c, cbit)) {
       int s1i, s1j, s2i, s2j;
       if (i < 1 && r < 1) {  // SW
         s1i = r, s1j = 1 - i, s2i = 1 - r, s2j = i;
@@ -357,8 +379,8 @@ FV3T_HD void adv5_issue_q(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T,
 // software-pipelined schedule of adv5_block uses.
 // EX selects the reference's own operation order (divisions by ra_x / ra_y / dp2, no shared reciprocals); instantiated in a
 // translation unit built with -fmad=false it is bit-identical to the FMA-free oracle (and to the strict k_advect2).
-template <class T, int OI, int OO, int PH, bool YE, bool EX = false>
-FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
+template <class T, int OI, int OO, int PH, bool YE, bool EX = false, class P>
+FV3T_HD void adv5_phase1(const P& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
   const int nd = c.nd;
   const int cc = r - 2;
   const Pair<T> y2 = A5P(v, A5_Y2, PH);  // zero outside the faces 1..n+1 (k_prep5, TMA zero fill)
@@ -383,8 +405,8 @@ FV3T_HD void adv5_phase1(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   A5XROW(s, A5X_QI + (PH & 1))[0] = qi;
 }
 
-template <class T, int OI, int OO, int PH, bool XE>
-FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
+template <class T, int OI, int OO, int PH, bool XE, class P>
+FV3T_HD void adv5_phase2(const P& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, int r) {
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
@@ -401,8 +423,8 @@ FV3T_HD void adv5_phase2(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   A5XROW(s, A5X_DO)[0] = ppm_pre<T, OO, XE>(i, nxx, qb, dxa_o);
 }
 
-template <class T, int OI, int OO, int PH, bool XE, bool EX = false>
-FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
+template <class T, int OI, int OO, int PH, bool XE, bool EX = false, class P>
+FV3T_HD void adv5_phase3(const P& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
   const int nd = c.nd;
   const int rr = XE ? clampi(r, -2, c.n + 3) : r;
   const int o = XE ? clampi(r - 3, 1, c.n) : r - 3;
@@ -425,8 +447,8 @@ FV3T_HD void adv5_phase3(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, 
   s.qys[(A5V_FX2 + PH) * A5_GW] = fx2;
 }
 
-template <class T, int OI, int OO, int PH, bool YE, bool EX = false>
-FV3T_HD void adv5_phase4(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
+template <class T, int OI, int OO, int PH, bool YE, bool EX = false, class P>
+FV3T_HD void adv5_phase4(const P& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t, const A5View<T>& v, int r) {
   const int n = c.n, nd = c.nd;
   const int cc = r - 2, o = r - 3;
   const T* dya = p.dya + c.tileoff + t.pix;
@@ -527,8 +549,8 @@ template <bool ONEG> __device__ __forceinline__ void a5_group_sync(int g) {
 // (phases 1-2-3-4 in sequence, three barriers) spent 2.6 of 9.4 stall cycles per issued instruction waiting on fixed-latency
 // FP64 dependencies and 0.8 at barriers (profiles/r02_advect5_v1_ncu.txt).  vp / v / vn: staged boxes of the previous, this and
 // the next block (phase 4 of step r0-1 reads the previous box, phase 1 of step r0+4 the next one).
-template <class T, int OI, int OO, bool YE, bool XE, bool ONEG, bool EX>
-__device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
+template <class T, int OI, int OO, bool YE, bool XE, bool ONEG, bool EX, class P>
+__device__ __forceinline__ void adv5_block(const P& p, const Adv5Cta& c, Adv5State<T, OI, OO>& s, const Adv3Thr& t,
                                            const A5View<T>& vp, const A5View<T>& v, const unsigned char* next_stage, uint64_t* full_next,
                                            unsigned par_next, uint64_t* empty_prev, int r0, int g, int gtid) {
   // ---- step r0 (PH 0)
@@ -577,8 +599,8 @@ __device__ __forceinline__ void adv5_block(const Adv5Params<T>& p, const Adv5Cta
   a5_group_sync<ONEG>(g);
 }
 
-template <class T, int OI, int OO, int NTHR, int MINB, bool EX = false>
-__global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ Adv5Params<T> p, const __grid_constant__ Adv5Maps maps) {
+template <class T, int OI, int OO, int NTHR, int MINB, bool EX = false, class P = Adv5Params<T>>
+__global__ void __launch_bounds__(NTHR, MINB) k_advect5(const __grid_constant__ P p, const __grid_constant__ Adv5Maps maps) {
   extern __shared__ __align__(128) unsigned char smem5[];
   using S = A5Stage<T>;
   const int strip = blockIdx.x, levc = blockIdx.y;

@@ -771,16 +771,24 @@ template <class T> int Impl<T>::substep(int it, int hord, T lim_fac) {
     p.iq0 = 0;
     p.nql = nq_cur;
     p.lim_fac = lim_fac;
-    for (int t = 0; t < nt; ++t) p.sub[t] = subflags[t];
     if (coef_wanted && it == 1 && !prof) {
       const int rcs = launch_coef_side();
       if (rcs) return rcs;
     }
     kbegin();
-    if (exact5)
+    if (sub_L) {  // the instantiations that look at the edge / corner flags of the resident sub-domains
+      fv3t::Adv5ParamsSub<T> ps{};
+      static_cast<fv3t::Adv5Params<T>&>(ps) = p;
+      for (int t = 0; t < nt; ++t) ps.sub[t] = subflags[t];
+      if (exact5)
+        CK(fv3t::exact_advect5_sub<T>(ps, maps5, hord, nt * npz, stream));
+      else
+        CK(fv3t::fast_advect5_sub<T>(ps, maps5, hord, nt * npz, stream));
+    } else if (exact5) {
       CK(fv3t::exact_advect5<T>(p, maps5, hord, nt * npz, stream));
-    else
+    } else {
       CK(fv3t::fast_advect5<T>(p, maps5, hord, nt * npz, stream));
+    }
     kend(KC_ADVECT);
     return apply_damping(it, false);  // mfx, mfy are scaled by finish() on this path
   }

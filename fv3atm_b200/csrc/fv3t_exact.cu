@@ -8,7 +8,7 @@
 
 namespace fv3t {
 
-template <class T> cudaError_t exact_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+template <class T, class P> static cudaError_t exact_dispatch(P p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
   switch (hord) {
     case 8: return launch5_ord<T, 8, 8, true>(p, m, nlev, stream);
     case 10: return launch5_ord<T, 8, 10, true>(p, m, nlev, stream);  // ord_in = 8 when hord == 10 (tp_core.F90:157-161)
@@ -29,12 +29,32 @@ template <class T> cudaError_t exact_advect5(Adv5Params<T> p, const Adv5Maps& m,
     default: return cudaErrorInvalidValue;
   }
 }
+template <class T> cudaError_t exact_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+  return exact_dispatch<T>(p, m, hord, nlev, stream);
+}
+template <class T> cudaError_t exact_advect5_sub(Adv5ParamsSub<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+  return exact_dispatch<T>(p, m, hord, nlev, stream);
+}
 
+// one object per precision and per parameter type (whole tiles / sub-tile contexts), built in parallel: FV3T_INST_F64 / _F32 and
+// FV3T_INST_WHOLE / _SUB select; with none of them defined everything is instantiated
+#if defined(FV3T_INST_WHOLE) || !defined(FV3T_INST_SUB)
+#define FV3T_EXACT_WHOLE(T) template cudaError_t exact_advect5<T>(Adv5Params<T>, const Adv5Maps&, int, int, cudaStream_t);
+#else
+#define FV3T_EXACT_WHOLE(T)
+#endif
+#if defined(FV3T_INST_SUB) || !defined(FV3T_INST_WHOLE)
+#define FV3T_EXACT_SUB(T) template cudaError_t exact_advect5_sub<T>(Adv5ParamsSub<T>, const Adv5Maps&, int, int, cudaStream_t);
+#else
+#define FV3T_EXACT_SUB(T)
+#endif
 #if defined(FV3T_INST_F64) || !defined(FV3T_INST_F32)
-template cudaError_t exact_advect5<double>(Adv5Params<double>, const Adv5Maps&, int, int, cudaStream_t);
+FV3T_EXACT_WHOLE(double)
+FV3T_EXACT_SUB(double)
 #endif
 #if defined(FV3T_INST_F32) || !defined(FV3T_INST_F64)
-template cudaError_t exact_advect5<float>(Adv5Params<float>, const Adv5Maps&, int, int, cudaStream_t);
+FV3T_EXACT_WHOLE(float)
+FV3T_EXACT_SUB(float)
 #endif
 
 }  // namespace fv3t

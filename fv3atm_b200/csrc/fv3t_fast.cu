@@ -124,13 +124,19 @@ template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T
   return encode_plane_map<T>(&m->rarea, p.RAREA, PP, nd, p.ntiles, 1);
 }
 
-template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+template <class T, class P> static cudaError_t fast_dispatch(P p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
   switch (hord) {
     case 8: return launch5_ord<T, 8, 8, false>(p, m, nlev, stream);
     case 11: return launch5_ord<T, 11, 11, false>(p, m, nlev, stream);
     case 2: return launch5_ord<T, 2, 2, false>(p, m, nlev, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+  return fast_dispatch<T>(p, m, hord, nlev, stream);
+}
+template <class T> cudaError_t fast_advect5_sub(Adv5ParamsSub<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream) {
+  return fast_dispatch<T>(p, m, hord, nlev, stream);
 }
 
 // ---- k_remap4 ---------------------------------------------------------------------------------------------------------------
@@ -241,6 +247,7 @@ template <class T> cudaError_t fast_remap3(const Remap3Params<T>& p, int akord, 
   template cudaError_t fast_pad_plane<T>(T*, const T*, int, int, int, cudaStream_t);                                  \
   template cudaError_t fast_advect5_maps<T>(Adv5Maps*, const Adv5Params<T>&, int);                                    \
   template cudaError_t fast_advect5<T>(Adv5Params<T>, const Adv5Maps&, int, int, cudaStream_t);                       \
+  template cudaError_t fast_advect5_sub<T>(Adv5ParamsSub<T>, const Adv5Maps&, int, int, cudaStream_t);                \
   template size_t remap4_coef_bytes<T>(int, int);                                                                     \
   template cudaError_t fast_remap_coef4<T>(const Remap4Params<T>&, cudaStream_t);                                     \
   template cudaError_t fast_remap4<T>(Remap4Params<T>, int, cudaStream_t);                                            \

@@ -43,6 +43,9 @@ template <class T> cudaError_t fast_advect5_maps(Adv5Maps* m, const Adv5Params<T
 template <class T> cudaError_t fast_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
 // the reference's operation order, bit-identical to the FMA-free oracle (fv3t_exact.cu, -fmad=false); needs k_prep5 with exact = 1
 template <class T> cudaError_t exact_advect5(Adv5Params<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
+// the same two for sub-tile contexts (fv3t_dims.sub_layout): the edge / corner flags of the resident sub-domains ride in p.sub
+template <class T> cudaError_t fast_advect5_sub(Adv5ParamsSub<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
+template <class T> cudaError_t exact_advect5_sub(Adv5ParamsSub<T> p, const Adv5Maps& m, int hord, int nlev, cudaStream_t stream);
 
 // ---- lanes-over-levels remap (fv3t_remap4.cuh): km <= 127, mapn_tracer form, uniform abs(kord) in fast_kord_ok ----
 template <class T> size_t remap4_coef_bytes(int n, int ntiles);

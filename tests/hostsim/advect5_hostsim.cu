@@ -44,8 +44,8 @@ template <class T> static void fill_stage(const Adv5Params<T>& p, int strip, int
 
 // one block of four row steps in the product's two-interval schedule (adv5_block): interval 1 = phase 2 of step s + phase 4 of
 // step s-1, interval 2 = phase 3 of step s + phase 1 of step s+1; a barrier (= end of a loop over the threads) after each
-template <class T, int OI, int OO, bool EX> struct Sim {
-  const Adv5Params<T>& p;
+template <class T, int OI, int OO, bool EX, class P> struct Sim {
+  const P& p;
   const Adv5Cta& c;
   std::vector<Adv5State<T, OI, OO>>& st;
   const std::vector<Adv3Thr>& th;
@@ -70,7 +70,7 @@ template <class T, int OI, int OO, bool EX> struct Sim {
   }
 };
 
-template <class T, int OI, int OO, bool EX> static void run_substep(const Adv5Params<T>& p) {
+template <class T, int OI, int OO, bool EX, class P> static void run_substep(const P& p) {
   const int n = p.n;
   const int strips = (n + A5_W - 1) / A5_W;
   const int nblocks = a5_nblocks(n);
@@ -85,7 +85,7 @@ template <class T, int OI, int OO, bool EX> static void run_substep(const Adv5Pa
       for (int iq = p.iq0; iq < p.iq0 + p.nql; ++iq) {
         Adv5Cta c;
         if (!adv5_make_cta<T>(p, strip, levc, iq, c)) continue;
-        Sim<T, OI, OO, EX> sim{p, c, st, th};
+        Sim<T, OI, OO, EX, P> sim{p, c, st, th};
         fill_stage<T>(p, strip, levc, 0, sg);
         for (int tid = 0; tid < A5_GW; ++tid) {
           th[tid] = adv5_thread(c, tid);
@@ -115,29 +115,38 @@ template <class T, int OI, int OO, bool EX> static void run_substep(const Adv5Pa
       }
 }
 
-// the instantiations the product builds: fast for fv3t::fast_hord_ok, exact for every scheme
-template <class T, bool EX> static int dispatch(const Adv5Params<T>& p, int hord) {
+// the instantiations the product builds: fast for fv3t::fast_hord_ok, exact for every scheme.  With the sub-tile parameter type
+// (the instantiations of sub-tile contexts) only the schemes the sub-mosaic tests run, to bound the build time of this harness.
+template <class T, bool EX, class P> static int dispatch(const P& p, int hord) {
   switch (hord) {
     case 8: run_substep<T, 8, 8, EX>(p); return 0;
-    case 11: run_substep<T, 11, 11, EX>(p); return 0;
-    case 2: run_substep<T, 2, 2, EX>(p); return 0;
   }
-  if (!EX) return 1;
-  switch (hord) {
-    case 10: run_substep<T, 8, 10, true>(p); break;
-    case 9: run_substep<T, 9, 9, true>(p); break;
-    case 12: run_substep<T, 12, 12, true>(p); break;
-    case 13: run_substep<T, 13, 13, true>(p); break;
-    case 7: run_substep<T, 7, 7, true>(p); break;
-    case 5: run_substep<T, 5, 5, true>(p); break;
-    case -5: run_substep<T, -5, -5, true>(p); break;
-    case 6: run_substep<T, 6, 6, true>(p); break;
-    case 1: run_substep<T, 1, 1, true>(p); break;
-    case 3: run_substep<T, 3, 3, true>(p); break;
-    case 4: run_substep<T, 4, 4, true>(p); break;
-    default: return 1;
+  if constexpr (!P::SUB) {
+    switch (hord) {
+      case 11: run_substep<T, 11, 11, EX>(p); return 0;
+      case 2: run_substep<T, 2, 2, EX>(p); return 0;
+    }
   }
-  return 0;
+  if constexpr (EX) {
+    switch (hord) {
+      case 10: run_substep<T, 8, 10, true>(p); return 0;
+      case 13: run_substep<T, 13, 13, true>(p); return 0;
+      case 5: run_substep<T, 5, 5, true>(p); return 0;
+      case -5: run_substep<T, -5, -5, true>(p); return 0;
+    }
+    if constexpr (!P::SUB) {
+      switch (hord) {
+        case 9: run_substep<T, 9, 9, true>(p); return 0;
+        case 12: run_substep<T, 12, 12, true>(p); return 0;
+        case 7: run_substep<T, 7, 7, true>(p); return 0;
+        case 6: run_substep<T, 6, 6, true>(p); return 0;
+        case 1: run_substep<T, 1, 1, true>(p); return 0;
+        case 3: run_substep<T, 3, 3, true>(p); return 0;
+        case 4: run_substep<T, 4, 4, true>(p); return 0;
+      }
+    }
+  }
+  return 1;
 }
 
 // q [6, nq, npz, nd, nd] in/out; dp1 [6, npz, nd, nd] in/out; cx, cy, mfx, mfy in/out (scaled when nsplt != 1)
@@ -170,10 +179,10 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
         const int64_t d = halo_dst[e], s = halo_src[e];
         q[(d / plane) * tile_stride + pl * plane + d % plane] = q[(s / plane) * tile_stride + pl * plane + s % plane];
       }
-    // one resident "tile" (whole tile or sub-domain) at a time: Adv5Params carries the flags of at most six
+    // one resident "tile" (whole tile or sub-domain) at a time
     for (int t = 0; t < nt; ++t) {
       const size_t so = (size_t)t * npz * nd * PP;
-      Adv5Params<T> p{};
+      Adv5ParamsSub<T> p{};
       p.qin = q + (size_t)t * tile_stride;
       p.qout = qb.data() + (size_t)t * tile_stride;
       p.X2 = X2.data() + so;
@@ -198,8 +207,15 @@ static int tracer_2d_sim(int n, int npz, int nq, T* q, T* dp1, T* mfx, T* mfy, T
       p.iq0 = 0;
       p.nql = nq;
       p.lim_fac = lim_fac;
-      if (sub) p.sub[0] = A5Sub{sub[5 * t], sub[5 * t + 1], sub[5 * t + 2], sub[5 * t + 3], sub[5 * t + 4]};
-      if (exact ? dispatch<T, true>(p, hord) : dispatch<T, false>(p, hord)) return 1;
+      int rc;
+      if (sub) {  // the parameter type, and with it the instantiations, of a sub-tile context
+        p.sub[0] = A5Sub{sub[5 * t], sub[5 * t + 1], sub[5 * t + 2], sub[5 * t + 3], sub[5 * t + 4]};
+        rc = exact ? dispatch<T, true>(p, hord) : dispatch<T, false>(p, hord);
+      } else {
+        const Adv5Params<T>& pw = p;
+        rc = exact ? dispatch<T, true>(pw, hord) : dispatch<T, false>(pw, hord);
+      }
+      if (rc) return 1;
     }
     for (int t = 0; t < nt; ++t)
       for (int iq = 0; iq < nq; ++iq)
