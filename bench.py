@@ -77,14 +77,42 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  The values are the ones `nvidia-smi --query-gpu=clocks.sm,
+    clocks.max.sm,clocks_event_reasons.*` prints, read through NVML in this process every 20 ms: a polling `nvidia-smi -lms`
+    child initialises NVML for every GPU of the box while the kernels run and takes the driver's locks for each query, which on a
+    multi-GPU step of ~30 ms showed up as ~5 ms per step (profiles/r02_bench_8gpu_*).  Falls back to the nvidia-smi child when
+    pynvml is missing."""
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nv = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _physical(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
 
     def start(self):
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -95,11 +123,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while True:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, why))
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.02):
+                return
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.th.join(timeout=1)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted(nm for nm, bit in self.BITS.items() if any(r[1] & bit for r in self.rows))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm),
+                    "source": "NVML (the values nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.* reports), every 20 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -122,7 +172,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def alg_bytes(w, nq, S=1.0):

@@ -328,8 +328,18 @@ class SubMosaicStep:
         scatter = lambda c, lt, offs, buf, at, stride: self.ctxs[c].halo_scatter(it, lt, self._list(c, offs), buf.data_ptr() + at * esz, stride)
         run_exchange(self.plan, self.npz * self.nq, self.copy_buf, self.sbuf, self.rbuf, gather, scatter, self.group)
 
+    def _mark(self, name):
+        """phase marks on the stream (bench diagnostics: SubMosaicStep.trace = [] switches them on)"""
+        tr = getattr(self, "trace", None)
+        if tr is not None:
+            import time
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record(self.stream)
+            tr.append((name, e, time.perf_counter()))
+
     def tracer_2d(self, hord: int, q_split: int = 0, lim_fac: float = 1.0) -> int:
         torch = self.torch
+        self._mark("start")
         # The halo update of the first sub-step needs neither cmax nor ksplt (every level takes part, and outside a tracer_2d call
         # every level lives in the current buffer): it is queued FIRST, behind whatever the stream is still running, so that its
         # launches and the NCCL transfer overlap the host round trips of the cmax reduction instead of following them.
@@ -337,6 +347,7 @@ class SubMosaicStep:
         early = getattr(self, "_primed", False)
         if early:
             self.exchange(1)
+        self._mark("halo1")
         cm = None
         for ctx in self.ctxs:
             c = ctx.tracer_2d_begin(self.nq, q_split)
@@ -350,6 +361,7 @@ class SubMosaicStep:
                 self.cmax_dev.copy_(torch.from_numpy(np.ascontiguousarray(cm)))
                 dist.all_reduce(self.cmax_dev, op=dist.ReduceOp.MAX, group=self.group)
                 cm = self.cmax_dev.cpu().numpy()
+        self._mark("cmax")
         nsplt = 0
         for ctx in self.ctxs:
             nsplt = ctx.tracer_2d_set_cmax(cm, q_split)
@@ -360,11 +372,13 @@ class SubMosaicStep:
                 ctx.tracer_2d_substep(it, hord, lim_fac)
         for ctx in self.ctxs:
             ctx.tracer_2d_finish()
+        self._mark("advect")
         return nsplt
 
     def remap(self, kord, fill=True):
         for ctx in self.ctxs:
             ctx.remap_tracers_resident(self.nq, kord, fill)
+        self._mark("remap")
 
     def close(self):
         for ctx in self.ctxs:
@@ -485,6 +499,21 @@ def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
                 dist.all_reduce(run.cmax_dev, op=dist.ReduceOp.MAX)
                 run.cmax_dev.cpu()
 
+    # phase marks of three traced steps: GPU time between the marks (events on the stream) and host time between them
+    phases = None
+    run.trace = []
+    for _ in range(3):
+        one()
+    barrier()
+    tr, run.trace = run.trace, None
+    if rank == 0:
+        acc = {}
+        for (n0, ev0, h0), (n1, ev1, h1) in zip(tr, tr[1:]):
+            a = acc.setdefault(f"{n0}->{n1}", [0.0, 0.0, 0])
+            a[0] += ev0.elapsed_time(ev1)
+            a[1] += (h1 - h0) * 1e3
+            a[2] += 1
+        phases = {k: {"gpu_ms": round(v[0] / v[2], 3), "host_ms": round(v[1] / v[2], 3)} for k, v in acc.items()}
     exchange_ms = timed(lambda: run.exchange(1))
     cmax_ms = timed(cmax_only)
     for c in run.ctxs:
@@ -570,7 +599,7 @@ def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
                            "halo": f"per sub-step one packed NCCL send/recv per peer pair ({len(run.plan.sends)} peers of rank 0, {run.halo_bytes} B sent by "
                                    f"rank 0: side halos + diagonal blocks as gather lists) + all-reduce(max) of cmax",
                            "halo_bytes_sent_per_rank_and_substep": run.halo_bytes, "halo_update_ms": exchange_ms, "cmax_reduction_ms": cmax_ms,
-                           "kernel_ms_per_step_by_rank": kernel_ms_by_rank,
+                           "kernel_ms_per_step_by_rank": kernel_ms_by_rank, "rank0_phases": phases,
                            "nsplt": int(nsplt), "updates_per_step": updates,
                            "l2": "inputs (GBs per rank) far exceed the 126 MB L2; no flush needed"},
                 "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": None, "clocks": clocks}
