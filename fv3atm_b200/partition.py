@@ -271,14 +271,14 @@ def bench_face_sharded(args, rank: int, world: int, local_rank: int, prefer: str
             step.remap(kord, fill=True)
             return ns
 
+        # (the sampler initialises NVML: before the warm-up, so that rank 0 does not enter the timed region late)
+        sampler = args.clock_sampler(local_rank) if rank == 0 and getattr(args, "clock_sampler", None) else None
         nsplt = 1
         for _ in range(max(args.warmup, 3)):
             nsplt = one()
         stream.synchronize()
         dist.barrier()
-        sampler = None
-        if rank == 0 and getattr(args, "clock_sampler", None):
-            sampler = args.clock_sampler(local_rank)
+        if sampler:
             sampler.start()
         l0 = ctx.kernel_launches()
         ctx.timer_start()

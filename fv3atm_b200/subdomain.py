@@ -449,13 +449,13 @@ def bench_submosaic(args, rank: int, world: int, local_rank: int) -> int:
         if world > 1:
             dist.barrier()
 
+    # (the sampler initialises NVML: before the warm-up, so that rank 0 does not enter the timed region late)
+    sampler = args.clock_sampler(local_rank) if rank == 0 and getattr(args, "clock_sampler", None) else None
     nsplt = 1
     for _ in range(max(args.warmup, 3)):
         nsplt = one()
     barrier()
-    sampler = None
-    if rank == 0 and getattr(args, "clock_sampler", None):
-        sampler = args.clock_sampler(local_rank)
+    if sampler:
         sampler.start()
     l0 = sum(c.kernel_launches() for c in run.ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
