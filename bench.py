@@ -382,8 +382,7 @@ def main():
         sampler.start()
     l0 = ctx.kernel_launches()
     ctx.timer_start()
-    for _ in range(args.steps):
-        step()
+    nsplt_steps = [step() for _ in range(args.steps)]
     ms = ctx.timer_stop_ms()
     launches = ctx.kernel_launches() - l0
     barrier()
@@ -528,7 +527,12 @@ def main():
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64" if w == 8 else "f32", "data": "synthetic",
                 "config": {"workload": workload, "parallelism": f"tracer-group x{world}" if world > 1 else "single GPU, 6 faces resident",
-                           "nsplt": int(nsplt), "l2": "inputs (tens of GB) far exceed the 126 MB L2; no flush needed",
+                           # tracer_2d scales the resident cx, cy, mfx, mfy by 1/ksplt in place (fv_tracer2d.F90:463-481): with
+                           # --courant > 1 the Courant numbers decay from call to call, so the sub-step count of EVERY timed step is
+                           # reported and a varying one is flagged (the default Courant number 0.7 gives nsplt = 1 throughout)
+                           "nsplt": int(nsplt_steps[-1]) if nsplt_steps else int(nsplt), "nsplt_of_every_timed_step": [int(v) for v in nsplt_steps],
+                           **({"warning": "nsplt varies over the timed steps: the value describes a decaying workload"} if len(set(nsplt_steps)) > 1 else {}),
+                           "l2": "inputs (tens of GB) far exceed the 126 MB L2; no flush needed",
                            "updates_per_step": updates_rank * world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity}
         if e2e_note:

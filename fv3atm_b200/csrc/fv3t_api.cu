@@ -164,6 +164,7 @@ template <class T> struct Impl {
   int* strip_halo[6][4] = {};
   EdgeMap maps[6][4];
   int local_of[6];  // global tile (0-based) -> local slot or -1
+  int nq_layout = 0;           // tracer count the resident q was laid out for by the last host upload (0: written through device pointers)
   int sub_L = 0;               // sub-tile context: layout L x L per tile (0: whole tiles); flags per resident sub-domain
   fv3t::A5Sub subflags[6];
   std::vector<int*> lists;     // gather / scatter lists (fv3t_halo_list_create)
@@ -422,7 +423,7 @@ template <class T> int Impl<T>::upload(int f, const T* h, int nq) {
   if (f == FV3T_Q && (nq < 1 || nq > nqmax)) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
   CK(cudaSetDevice(device));
   CK(cudaMemcpyAsync(dptr, h, field_elems(f, nq) * sizeof(T), cudaMemcpyHostToDevice, stream));
-  if (f == FV3T_Q) nq_cur = nq;
+  if (f == FV3T_Q) nq_cur = nq_layout = nq;
   if (f == FV3T_PE) coef_ready = coef_wanted = false;
   return 0;
 }
@@ -440,6 +441,8 @@ template <class T> int Impl<T>::download(int f, T* h, int nq) {
 // steps A-B up to the local cmax (fv_tracer2d.F90:387-427); xfx/yfx are not materialised (see fv3t_advect.cuh)
 template <class T> int Impl<T>::begin(int nq, int q_split, T* cmax_local) {
   if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  // nq is the tile stride of q: a count other than the one the resident tracers were uploaded with would address other planes
+  if (nq_layout && nq != nq_layout) return fail("fv3tracer: nq = %d, but the resident tracers were uploaded as %d per tile", nq, nq_layout);
   CK(cudaSetDevice(device));
   nq_cur = nq;
   if (q_split == 0) {
@@ -1128,6 +1131,7 @@ template <class T, int G, bool MAPN> int launch_remap2(Impl<T>& c, const fv3t::R
 // writes q[cur^1]; a whole-tile call (j_count == n) makes the written buffer the current one.
 template <class T> int Impl<T>::remap_resident(int nq, const int* kord, int fill, int j_first, int j_count, const T* pe2_ext, const T* dp2_ext) {
   if (nq < 1 || nq > nqmax) return fail("fv3tracer: nq = %d outside 1..nq_max = %d", nq, nqmax);
+  if (nq_layout && nq != nq_layout) return fail("fv3tracer: nq = %d, but the resident tracers were uploaded as %d per tile", nq, nq_layout);
   if (!have_vertical && !pe2_ext) return fail("fv3tracer: set_vertical(ak, bk, ptop) has not been called");
   CK(cudaSetDevice(device));
   CK(cudaMemcpyAsync(kord_d, kord, nq * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1307,7 +1311,7 @@ int Impl<T>::tracer_step(T* hq, T* hdp1, T* hmfx, T* hmfy, T* hcx, T* hcy, const
     ev_up.push_back(a);
     ev_done.push_back(b);
   }
-  nq_cur = nq;
+  nq_cur = nq_layout = nq;
   if ((rc = prepare(hord))) return rc;  // k_prep5 / k_prep3 (nsplt == 1: nothing is scaled in place)
   if ((rc = remap_alloc())) return rc;
   const int c0 = cur;                   // per tracer: advect q[c0] -> q[c0^1], remap q[c0^1] -> q[c0]
@@ -1642,6 +1646,7 @@ extern "C" int fv3t_device_count(void) {
     if (!I->row_buf) CK(cudaMalloc((void**)&I->row_buf, (npe2 + ndp2) * sizeof(REAL)));                                        \
     CK(cudaMemcpyAsync(I->row_buf, pe2, npe2 * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                              \
     CK(cudaMemcpyAsync(I->row_buf + npe2, dp2, ndp2 * sizeof(REAL), cudaMemcpyHostToDevice, I->stream));                       \
+    I->nq_layout = nq; /* the rows were just laid out for nq tracers */                                                        \
     int rc = I->remap_resident(nq, kord, fill, j - 1, 1, I->row_buf, I->row_buf + npe2);                                       \
     if (rc) return rc;                                                                                                         \
     CK(cudaMemcpy2DAsync(q1 + (size_t)(j + 2) * nd, pl * sizeof(REAL), I->q[I->cur ^ 1] + (size_t)(j + 2) * nd,                \

@@ -163,7 +163,9 @@ int fv3t_device_count(void);
                              const REAL* ak, const REAL* bk, REAL ptop, REAL* delp, int nq, int hord, int q_split,          \
                              REAL lim_fac, const int* kord_tr, int fill, int* nsplt_out);                                    \
                                                                                                                         \
-  /* Device-resident operation (north star: tracers, Courant numbers, mass fluxes and delp stay in HBM). */            \
+  /* Device-resident operation (north star: tracers, Courant numbers, mass fluxes and delp stay in HBM).  nq is the tile     \
+     stride of the resident q: the resident calls must be given the count of the last upload(FV3T_Q) (anything else is an      \
+     error); a host that fills q through fv3t_device_ptr lays it out as (isd:ied, jsd:jed, npz, nq) per tile itself. */        \
   int fv3t_##P##_upload(fv3t_ctx* ctx, int field, const REAL* host, int nq);                                            \
   int fv3t_##P##_download(fv3t_ctx* ctx, int field, REAL* host, int nq);                                                \
   int fv3t_##P##_set_vertical(fv3t_ctx* ctx, const REAL* ak, const REAL* bk, REAL ptop);                                \

@@ -500,3 +500,20 @@ def test_tracer_damping_deln_flux(oracle, case_factory, nord, courant, mode):
     assert np.array_equal(out["dp1"][..., sl, sl], plain["dp1"][..., sl, sl])
     for k in ("cx", "cy", "mfx", "mfy"):
         assert np.array_equal(out[k], plain[k]), k
+
+
+def test_resident_calls_reject_a_tracer_count_other_than_the_uploaded_one(case_factory):
+    """nq is the tile stride of the resident q: tracer_2d_resident / remap_tracers_resident with another count than the upload's
+    would address other planes -- an error, not a silent wrong answer."""
+    from fv3atm_b200.lib import Fv3tError
+    case = case_factory(24, 16, 9, "float64")
+    ctx = TracerContext(case.n + 1, case.npz, case.nq, case.metrics(), dtype=case.dtype)
+    for f in ("q", "dp1", "mfx", "mfy", "cx", "cy", "pe"):
+        ctx.upload(f, getattr(case, f), case.nq)
+    ctx.set_vertical(case.ak, case.bk, case.ptop)
+    with pytest.raises(Fv3tError, match="uploaded as 9"):
+        ctx.tracer_2d_resident(5, 8)
+    with pytest.raises(Fv3tError, match="uploaded as 9"):
+        ctx.remap_tracers_resident(6, 9, True)
+    assert ctx.tracer_2d_resident(case.nq, 8) >= 1
+    ctx.close()
