@@ -286,3 +286,77 @@ def test_scalar_profile_and_cs_profile_agree_where_they_share_the_algorithm(orac
     s = oracle.profile_col(0, a1, dp, iv=0, kord=kord)
     c = oracle.profile_col(1, a1, dp, iv=0, kord=kord)
     assert np.abs(s - c).max() <= 1e-12 * np.abs(a1).max()
+
+
+# ---- fv_tp_2d as an operator (tp_core.F90:110-249): both flux branches and both forms of deln_flux ---------------------------------
+def _tp2d_inputs(case, k, iq):
+    """ghosted q of one (level, tracer) and the operands tracer_2d itself builds for that level (fv_tracer2d.F90:387-405, 449-462)"""
+    import oracle_binding as ob
+    g = case.metrics()
+    n, nd = case.n, case.n + 6
+    dst, src = ob.halo_offsets(n)
+    stack = np.ascontiguousarray(case.q[:, iq, k]).reshape(-1).copy()
+    stack[dst] = stack[src]
+    q = stack.reshape(6, nd, nd)
+    crx, cry = case.cx[:, k], case.cy[:, k]
+    ss, dxa, dya, dx, dy, area = g["sin_sg"], g["dxa"], g["dya"], g["dx"], g["dy"], g["area"]
+    dyf = dy[..., 3:n + 4]
+    xfx = np.where(crx > 0, crx * dxa[..., 2:n + 3] * dyf * ss[:, 2, :, 2:n + 3], crx * dxa[..., 3:n + 4] * dyf * ss[:, 0, :, 3:n + 4])
+    dxf = dx[..., 3:n + 4, :]
+    yfx = np.where(cry > 0, cry * dya[..., 2:n + 3, :] * dxf * ss[:, 3, 2:n + 3, :], cry * dya[..., 3:n + 4, :] * dxf * ss[:, 1, 3:n + 4, :])
+    ra_x = area[:, :, 3:n + 3] + xfx[..., :-1] - xfx[..., 1:]
+    ra_y = area[:, 3:n + 3, :] + yfx[..., :-1, :] - yfx[..., 1:, :]
+    return g, q, crx, cry, xfx, yfx, ra_x, ra_y
+
+
+@pytest.mark.parametrize("hord", [8, 10, 5, 13])
+def test_fv_tp_2d_fluxes_reproduce_the_tracer_2d_update(oracle, case_factory, hord):
+    """The tracer branch of the operator, put through the flux-form update of fv_tracer2d.F90:533-541, is what tracer_2d does to
+    that level -- bit for bit: the operator restatement and the driver restatement pin each other."""
+    import oracle_binding as ob
+    case = case_factory(12, 8, 9, "float64")
+    ref = oracle.tracer_2d(case, hord=hord)
+    assert ref["nsplt"] == 1
+    k, iq, n = 3, 4, case.n
+    g, q, crx, cry, xfx, yfx, ra_x, ra_y = _tp2d_inputs(case, k, iq)
+    sl = slice(3, -3)
+    for t in range(6):
+        fx, fy, qo = ob.fv_tp_2d(q[t], crx[t], cry[t], hord, xfx[t], yfx[t], ra_x[t], ra_y[t], g["area"][t], g["dxa"][t], g["dya"][t],
+                                 mfx=case.mfx[t, k], mfy=case.mfy[t, k])
+        dp1, rarea = case.dp1[t, k, sl, sl], g["rarea"][t, sl, sl]
+        mfx, mfy = case.mfx[t, k], case.mfy[t, k]
+        dp2 = dp1 + (mfx[:, :-1] - mfx[:, 1:] + mfy[:-1, :] - mfy[1:, :]) * rarea
+        qn = (q[t, sl, sl] * dp1 + (fx[:, :-1] - fx[:, 1:] + fy[:-1, :] - fy[1:, :]) * rarea) / dp2
+        assert np.array_equal(qn, ref["q"][t, iq, k, sl, sl])
+        assert np.array_equal(qo[sl, sl], q[t, sl, sl])        # only the corner blocks of q are rewritten (dir = 1 view, :189)
+
+
+def test_fv_tp_2d_branch_without_mass_fluxes_and_uniform_field(oracle, case_factory):
+    """delp / vorticity branch (:236-242): fluxes are scaled by xfx, yfx; a uniform field gives exactly q * xfx -- with every
+    scheme, at the tile edges too -- and its del-n damping fluxes vanish (both forms of deln_flux, :1239-1387)."""
+    import oracle_binding as ob
+    case = case_factory(12, 8, 9, "float64")
+    g, q, crx, cry, xfx, yfx, ra_x, ra_y = _tp2d_inputs(case, 2, 0)
+    d6u, d6v, da_min = cs.damping_metrics(case.grid)
+    n = case.n
+    qu = np.full_like(q[0], 2.5)
+    for hord in (8, 10, 9, 6, -5, 1):
+        fx, fy, _ = ob.fv_tp_2d(qu, crx[0], cry[0], hord, xfx[0], yfx[0], ra_x[0], ra_y[0], g["area"][0], g["dxa"][0], g["dya"][0])
+        assert np.allclose(fx, 2.5 * xfx[0][3:n + 3, :], rtol=1e-13, atol=0) and np.allclose(fy, 2.5 * yfx[0][:, 3:n + 3], rtol=1e-13, atol=0)
+    for nord in (0, 1, 2):
+        for mass in (None, case.dp1[0, 2]):
+            kw = dict(rarea=g["rarea"][0], del6_u=d6u[0], del6_v=d6v[0], da_min=da_min, nord=nord, damp_c=0.15, mass=mass)
+            if mass is not None:
+                kw.update(mfx=case.mfx[0, 2], mfy=case.mfy[0, 2])
+            a = ob.fv_tp_2d(qu, crx[0], cry[0], 8, xfx[0], yfx[0], ra_x[0], ra_y[0], g["area"][0], g["dxa"][0], g["dya"][0], **kw)
+            kw.update(nord=-1)
+            b = ob.fv_tp_2d(qu, crx[0], cry[0], 8, xfx[0], yfx[0], ra_x[0], ra_y[0], g["area"][0], g["dxa"][0], g["dya"][0], **kw)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])     # no damping flux on a uniform field
+    # and on a non-uniform field the damping does act, in both forms
+    for mass in (None, case.dp1[0, 2]):
+        kw = dict(rarea=g["rarea"][0], del6_u=d6u[0], del6_v=d6v[0], da_min=da_min, damp_c=0.15, mass=mass)
+        if mass is not None:
+            kw.update(mfx=case.mfx[0, 2], mfy=case.mfy[0, 2])
+        a = ob.fv_tp_2d(q[0], crx[0], cry[0], 8, xfx[0], yfx[0], ra_x[0], ra_y[0], g["area"][0], g["dxa"][0], g["dya"][0], nord=1, **kw)
+        b = ob.fv_tp_2d(q[0], crx[0], cry[0], 8, xfx[0], yfx[0], ra_x[0], ra_y[0], g["area"][0], g["dxa"][0], g["dya"][0], nord=-1, **kw)
+        assert not np.array_equal(a[0], b[0])
