@@ -148,3 +148,17 @@ def test_product_ppm_functions_equal_the_oracle_line(ppm_sim, oracle):
         a = _product_flux(ppm_sim, q, c, iord)
         b = _oracle_flux(oracle, q, c, iord)
         assert np.array_equal(a, b), (iord, np.abs(a - b).max())
+
+
+def test_fortran_probe_reports_why_the_oracle_is_unpinned():
+    """oracle/probe_fortran.py: with no Fortran compiler the reference cannot be built into oracle/_ref, which is why the header of
+    the oracle says "parity unpinned"; if a compiler ever appears this test fails and asks for the real reference build."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "probe_fortran.py")], capture_output=True, text=True, check=True).stdout
+    info = json.loads(out.strip().splitlines()[-1])
+    assert set(info) == {"fortran_compilers", "reference_sources_present", "oracle_ref_buildable"}
+    assert not info["oracle_ref_buildable"], f"a Fortran compiler exists ({info['fortran_compilers']}): build oracle/_ref from the reference"
